@@ -1,0 +1,132 @@
+"""Import the UNMODIFIED reference (ManifoldRG/NEKO) in this container.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``neko_b200/``) imports this module.
+It exists so that (1) ``oracle/make_golden.py`` can run the real reference on seeded inputs and
+write the fixtures under ``tests/golden/`` and (2) ``tests/test_oracle_vs_reference.py`` can
+pin the restatement in ``oracle/gato_oracle.py`` against the reference whenever
+``/root/reference`` is mounted (it is NOT mounted on the GPU box).
+
+The reference was written for transformers 4.30.2 / torch 2.0.1 (``env.yml:8-36``); this image
+has transformers 5.x and lacks gymnasium, so a handful of in-memory shims are installed before
+``import gato.policy.gato_policy``.  No reference file is modified
+or copied.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("NEKO_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "gato", "policy", "gato_policy.py"))
+
+
+class _FakeTextTokenizer:
+    """Only ``vocab_size`` is read on the hot path (gato_policy.py:57-60)."""
+
+    def __init__(self, vocab_size: int = 50257):
+        self.vocab_size = vocab_size
+
+    def encode(self, s):  # pragma: no cover - not on the hot path
+        raise NotImplementedError("offline shim: no GPT-2 BPE tables in this container")
+
+    def decode(self, ids):  # pragma: no cover
+        raise NotImplementedError("offline shim: no GPT-2 BPE tables in this container")
+
+
+_installed = False
+_text_vocab = 50257
+
+
+def set_text_vocab(n: int) -> None:
+    """Vocabulary size reported by the shimmed AutoTokenizer (50257 = GPT-2)."""
+    global _text_vocab
+    _text_vocab = int(n)
+
+
+def install_shims() -> None:
+    global _installed
+    if _installed:
+        return
+    import transformers
+    import transformers.modeling_utils as mu
+    import transformers.pytorch_utils as pu
+
+    # (1)(2) names trajectory_gpt2.py:37-43 imports from modeling_utils
+    if not hasattr(mu, "Conv1D"):
+        mu.Conv1D = pu.Conv1D
+    for name in ("find_pruneable_heads_and_indices", "prune_conv1d_layer"):
+        if not hasattr(mu, name):
+            setattr(mu, name, getattr(pu, name, lambda *a, **k: None))
+    if not hasattr(mu, "SequenceSummary"):
+        import torch.nn as nn
+
+        class SequenceSummary(nn.Module):  # dead code on the hot path
+            def __init__(self, *a, **k):
+                super().__init__()
+
+        mu.SequenceSummary = SequenceSummary
+
+    # (3) transformers.utils.model_parallel_utils (removed in HF 5)
+    modname = "transformers.utils.model_parallel_utils"
+    if modname not in sys.modules:
+        try:
+            __import__(modname)
+        except Exception:
+            m = types.ModuleType(modname)
+            m.assert_device_map = lambda *a, **k: None
+            m.get_device_map = lambda *a, **k: {}
+            sys.modules[modname] = m
+
+    # (4) gymnasium: only touched inside predict_control (gato_policy.py:564-567)
+    if "gymnasium" not in sys.modules:
+        try:
+            import gymnasium  # noqa: F401
+        except Exception:
+            g = types.ModuleType("gymnasium")
+            sp = types.ModuleType("gymnasium.spaces")
+
+            class Box:  # noqa: D401
+                pass
+
+            class Discrete:
+                pass
+
+            class Env:
+                pass
+
+            sp.Box, sp.Discrete = Box, Discrete
+            g.spaces, g.Env = sp, Env
+            sys.modules["gymnasium"] = g
+            sys.modules["gymnasium.spaces"] = sp
+
+    # (5) AutoTokenizer.from_pretrained('gpt2') needs the hub; the hot path reads .vocab_size only
+    class _AutoTok:
+        @staticmethod
+        def from_pretrained(name, *a, **k):
+            return _FakeTextTokenizer(_text_vocab)
+
+    transformers.AutoTokenizer = _AutoTok
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+    import gato.transformers.trajectory_gpt2 as tg
+
+    # (6) HF-4.30.2 behaviour of init_weights / get_head_mask for a model without tied weights
+    tg.GPT2PreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    tg.GPT2Model.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    _installed = True
+
+
+def load_reference_policy_class():
+    """Returns the reference's ``GatoPolicy`` class (gato/policy/gato_policy.py:18)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    install_shims()
+    from gato.policy.gato_policy import GatoPolicy
+
+    return GatoPolicy
