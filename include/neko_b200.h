@@ -1,0 +1,200 @@
+/*
+ * neko_b200 -- C ABI of the B200-native Gato training hot path.
+ *
+ * The reference (ManifoldRG/NEKO) has no FFI: its hot path is the Python class
+ * gato/policy/gato_policy.py:18 (GatoPolicy) calling torch ops.  This header declares the
+ * operator-level entry points a maintainer binds (ctypes) to replace those
+ * torch call sites.  Every function cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns every buffer (outputs and workspaces included); nothing is allocated,
+ *     nothing synchronises, everything is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative NEKO_E* code otherwise; neko_last_error() gives the
+ *     thread-local message;  sm_100 only -- other devices get NEKO_EDEVICE (no CPU fallback);
+ *   - bf16 buffers are raw uint16_t bit patterns (__nv_bfloat16).
+ */
+#ifndef NEKO_B200_H
+#define NEKO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEKO_OK 0
+#define NEKO_EINVAL (-1)   /* bad argument (shape / alignment / null pointer) */
+#define NEKO_ECUDA (-2)    /* CUDA runtime / driver error                      */
+#define NEKO_EDEVICE (-3)  /* current device is not sm_100                     */
+
+int neko_version(void);
+const char* neko_last_error(void);
+/* 0 when the current CUDA device is a compute-capability-10.x part. */
+int neko_device_check(void);
+int neko_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tokenise + embed + interleave: GatoPolicy.tokenize_input_dicts, gato_policy.py:195-432,
+ * with ContinuousTokenizer.encode / mu_law (input_tokenizers.py:5-30) inlined.
+ * One descriptor per sample; the host packs all continuous values into `fvals`, all integer
+ * inputs (text ids, discrete obs / actions) into `ivals`.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct neko_sample_desc {
+  int32_t n_timesteps;   /* T                                                            */
+  int32_t n_patches;     /* image patches per timestep (ids 0, target 0)                 */
+  int32_t n_text;        /* text tokens per timestep (target 1)                          */
+  int32_t n_cobs;        /* continuous observation scalars per timestep (mu-law, tgt 0)  */
+  int32_t n_dobs;        /* discrete observation tokens per timestep (target 0)          */
+  int32_t n_cact;        /* continuous action scalars per timestep (no mu-law, tgt 1)    */
+  int32_t n_dact;        /* discrete action tokens per timestep (target 1)               */
+  int32_t seq_off;       /* left padding = S - T * tokens_per_timestep                   */
+  int32_t text_off;      /* offsets (elements) of this sample's [T, n_*] blocks          */
+  int32_t cobs_off;      /*   text/dobs/dact index ivals, cobs/cact index fvals          */
+  int32_t dobs_off;
+  int32_t cact_off;
+  int32_t dact_off;
+  int32_t patch_off;     /* first row of this sample in patch_emb [P_total, d]           */
+  int32_t reserved0;
+  int32_t reserved1;
+} neko_sample_desc;
+
+typedef struct neko_tok_params {
+  float mu;              /* 100   */
+  float M;               /* 256   */
+  int32_t n_bins;        /* 1024  */
+  int32_t cont_start;    /* token_starts['continuous'] = 50257, gato_policy.py:66-70 */
+  int32_t disc_start;    /* token_starts['discrete']   = 51281 */
+  int32_t vocab;         /* rows of embed_table */
+  int32_t use_pos;       /* add pos_embed_observation to observation tokens (:381-385) */
+  int32_t seq_len;       /* S: left-padded length (max over samples)                  */
+  int32_t width;         /* output row length (= S, or context_len with pad_seq)      */
+  int32_t ctx_rows;      /* rows of pos_table */
+} neko_tok_params;
+
+/* ids, masks and embeddings in one pass.  tokens int64 [B,width]; target/token masks fp32
+ * [B,width]; token_embeddings fp32 [B,width,d] (may be NULL: ids/masks only).
+ * err_flag (nullable, int32): set to 1 when an id falls outside [0,vocab). */
+int neko_tokenize_embed_fwd(const neko_sample_desc* descs, int B, int d, const neko_tok_params* host_params,
+                            const float* fvals, const int32_t* ivals, const float* patch_emb,
+                            const float* embed_table, const float* pos_table, const float* sep_vec,
+                            int64_t* tokens, float* target_masks, float* token_masks,
+                            float* token_embeddings, int32_t* err_flag, void* stream);
+
+/* Backward of the embedding half (autograd of gato_policy.py:275-393): scatter-adds into
+ * d_embed_table [vocab,d], d_pos_table [ctx_rows,d], d_sep [d] (all fp32, accumulated) and writes
+ * d_patch_emb [P_total,d] (nullable). */
+int neko_embed_bwd(const neko_sample_desc* descs, int B, int d, const neko_tok_params* host_params,
+                   const int64_t* tokens, const float* d_token_embeddings,
+                   float* d_embed_table, float* d_pos_table, float* d_sep, float* d_patch_emb,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (ln_1 / ln_2 / ln_f, trajectory_gpt2.py:323,353,779). x fp32 [N,d] -> y bf16.
+ * ------------------------------------------------------------------------------------------- */
+int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_bf16,
+                       float* mean, float* rstd, int N, int d, float eps, void* stream);
+/* dx_resid (fp32 [N,d]) += LN'(dy); optional bf16 copy of the updated dx_resid; dgamma/dbeta
+ * fp32 [d] are accumulated (caller zeroes them). */
+int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean,
+                       const float* rstd, float* dx_resid, uint16_t* dx_bf16, float* dgamma,
+                       float* dbeta, int N, int d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense GEMM on tcgen05 tensor cores (HF Conv1D addmm trajectory_gpt2.py:222,253,274,277;
+ * predict_token gato_policy.py:172; post_embedding_projection embeddings.py:53; and their
+ * autograd dgrad / wgrad).   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ).
+ * a_mn / b_mn = 0: operand is K-major (row m / n is contiguous in k, leading dimension ld);
+ *             = 1: operand is MN-major (stored [K, M] / [K, N] row-major, leading dimension ld).
+ * ------------------------------------------------------------------------------------------- */
+enum neko_epilogue {
+  NEKO_EPI_BF16 = 0,            /* C bf16 = acc (+bias)                                        */
+  NEKO_EPI_F32 = 1,             /* C fp32 = acc (+bias) (+= C when accumulate)                  */
+  NEKO_EPI_GELU_BF16 = 2,       /* C bf16 = acc+bias (pre-activation), C2 bf16 = gelu_erf(C)    */
+  NEKO_EPI_RESID_F32 = 3,       /* C fp32 = acc + bias + aux_f32[m,n]   (residual add)          */
+  NEKO_EPI_DGELU_BF16 = 4,      /* C bf16 = acc * gelu_erf'(aux_bf16[m,n])                      */
+  NEKO_EPI_RESID_F32_BF16 = 5   /* as 3, plus C2 bf16 copy of the result                        */
+};
+
+int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t lda, int a_mn, const uint16_t* B,
+                   int64_t ldb, int b_mn, int epilogue, void* C, int64_t ldc, void* C2, int64_t ldc2,
+                   const float* bias, const void* aux, int64_t ld_aux, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Causal self-attention with left padding (Attention._attn, trajectory_gpt2.py:163-188, with the
+ * additive -1e4 padding bias of :663-679 realised as a per-sample first valid key).
+ * qkv bf16 [B,S,3*H*dh] (q | k | v as c_attn emits them), out bf16 [B,S,H*dh], lse fp32 [B,H,S].
+ * Sample b attends keys in [first_valid[b], min(query, S_valid-1)]; rows outside [first_valid[b], S_valid)
+ * (left padding, right padding of --pad_seq) are written as zeros.
+ * ------------------------------------------------------------------------------------------- */
+int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out, float* lse,
+                       int B, int S, int S_valid, int H, int dh, void* stream);
+/* dqkv bf16 [B,S,3*H*dh]; delta fp32 [B,H,S] is caller-provided scratch. */
+int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse,
+                       const int32_t* first_valid, uint16_t* dqkv, float* delta, int B, int S, int S_valid,
+                       int H, int dh, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked cross entropy (gato_policy.py:174-186).  rows int32 [n_rows]: flat source positions
+ * b*S_width+s whose target is tokens[row+1]; loss = mean over rows (written to *loss).
+ * ------------------------------------------------------------------------------------------- */
+int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
+                       const int64_t* tokens, float* row_lse, float* row_loss, float* loss,
+                       void* stream);
+/* dlogits bf16 [*, ld_dlogits] rows listed in `rows` get (softmax - onehot) * (*gscale) / n_rows;
+ * the caller zero-fills the buffer beforehand.  gscale: device fp32 scalar (upstream d loss).
+ * ld_dlogits < 0 selects the COMPACT layout: row r of dlogits (pitch -ld_dlogits) receives rows[r]. */
+int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
+                       const int64_t* tokens, const float* row_lse, const float* gscale,
+                       uint16_t* dlogits, int64_t ld_dlogits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small memory-bound helpers around the GEMMs.
+ * ------------------------------------------------------------------------------------------- */
+int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+/* out[n] (+)= sum_m X[m,n]; X bf16 [M, ld]  (bias gradients of Conv1D / Linear). */
+int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, int accumulate, void* stream);
+/* rows: dst[i,:] = src[rows[i],:] (gather) or dst[rows[i],:] = src[i,:] (scatter), bf16 width n. */
+int neko_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* rows, int n_rows, int n,
+                          uint16_t* dst, int64_t ld_dst, void* stream);
+int neko_scatter_rows_add_f32(const uint16_t* src_bf16, int64_t ld_src, const int32_t* rows, int n_rows,
+                              int n, float* dst, int64_t ld_dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Image patch embedding: ImageEmbedding.forward / ResidualBlock_V2 (embeddings.py:28-61,111-131)
+ * up to (not including) post_embedding_projection, which is a neko_gemm_bf16 call.
+ * images: `n_img` frames [3,Himg,Wimg] of fp32 (is_u8=0) or uint8 (is_u8=1), 0..255.
+ * patches_out bf16 [n_img*n_h*n_w, 3*p*p]  (c p1 p2 flattening, embeddings.py:50).
+ * Saved for backward: gn_stats fp32 [P, groups, 2] (mean, rstd).
+ * ------------------------------------------------------------------------------------------- */
+int neko_patch_resblock_fwd(const void* images, int is_u8, int n_img, int Himg, int Wimg, int patch,
+                            int C, int groups, const float* conv1_w, const float* conv1_b,
+                            const float* gn_w, const float* gn_b, const float* conv2_w,
+                            const float* conv2_b, uint16_t* patches_out, float* gn_stats, void* stream);
+int neko_patch_resblock_bwd(const void* images, int is_u8, int n_img, int Himg, int Wimg, int patch,
+                            int C, int groups, const float* conv1_w, const float* conv1_b,
+                            const float* gn_w, const float* gn_b, const float* conv2_w,
+                            const float* gn_stats, const uint16_t* d_patches_bf16,
+                            float* d_conv1_w, float* d_conv1_b, float* d_gn_w, float* d_gn_b,
+                            float* d_conv2_w, float* d_conv2_b, void* stream);
+/* x[p,:] += row_tab[row_idx[p % (n_h*n_w) / n_w]] + col_tab[col_idx[p % n_w]] (embeddings.py:56-57,
+ * 102-110) on fp32 [P,d]; the bins are computed by the host with the reference's own torch calls. */
+int neko_patch_pos_add(float* x, int P, int d, int n_h, int n_w, const int32_t* row_idx,
+                       const int32_t* col_idx, const float* row_tab, const float* col_tab, void* stream);
+int neko_patch_pos_bwd(const float* dx, int P, int d, int n_h, int n_w, const int32_t* row_idx,
+                       const int32_t* col_idx, float* d_row_tab, float* d_col_tab, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser step (train.py:127-133, trainer.py:181-186): global-norm clip + AdamW over one flat
+ * fp32 parameter / gradient arena.
+ * ------------------------------------------------------------------------------------------- */
+int neko_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream);
+int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    const float* grad_sumsq, float max_norm, float grad_div, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEKO_B200_H */

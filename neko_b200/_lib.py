@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI in include/neko_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing or the device is not an sm_100
+part, every entry point raises.  (The parity oracle lives under oracle/ and is never imported here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libneko_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "neko_b200.h")
+
+
+class NekoError(RuntimeError):
+    pass
+
+
+class SampleDesc(C.Structure):
+    """neko_sample_desc (include/neko_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_timesteps", "n_patches", "n_text", "n_cobs", "n_dobs", "n_cact", "n_dact", "seq_off",
+        "text_off", "cobs_off", "dobs_off", "cact_off", "dact_off", "patch_off", "reserved0", "reserved1")]
+
+
+class TokParams(C.Structure):
+    """neko_tok_params (include/neko_b200.h)."""
+    _fields_ = [("mu", C.c_float), ("M", C.c_float)] + [(n, C.c_int32) for n in (
+        "n_bins", "cont_start", "disc_start", "vocab", "use_pos", "seq_len", "width", "ctx_rows")]
+
+
+EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_DGELU_BF16, EPI_RESID_F32_BF16 = range(6)
+
+_lib = None
+
+
+def declared_symbols():
+    """Every function include/neko_b200.h declares (used by the CPU-side export test)."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(neko_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NekoError(f"{LIB_PATH} is missing: run `python -m neko_b200.build` (or __graft_entry__.build()). "
+                        "There is no CPU fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.neko_last_error.restype = C.c_char_p
+    for name in declared_symbols():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        if name != "neko_last_error":
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _p(x):
+    """tensor / int / None -> void*"""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    return C.c_void_p(x.data_ptr())
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().neko_last_error().decode()
+        raise NekoError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_device():
+    check(load().neko_device_check(), "neko_device_check")

@@ -1,0 +1,147 @@
+// Masked cross entropy over the joint text + continuous + discrete vocabulary (gato_policy.py:174-186).
+//
+// The reference shifts logits/targets by one position, boolean-selects the rows where
+// token_masks[:, :-1] * token_target_masks[:, 1:] > 0 (a dynamic-shape gather that syncs the host) and
+// takes F.cross_entropy(mean).  Here the host already knows the row list from the tokenisation plan
+// (no sync); one CTA streams one selected logits row: online max / sum-exp in fp32, loss_i = lse - z[tgt].
+// Backward writes (softmax - onehot) * g / n_rows as bf16 straight into the dlogits operand of the head
+// dgrad / wgrad GEMMs.  HBM-bound: V*4 bytes read per selected row (+ V*2 written in backward).
+#include "common.cuh"
+
+namespace neko {
+
+constexpr int CE_THREADS = 256;
+
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  if (mn == -INFINITY) { m = mn; s = 0.f; return; }
+  s = s * __expf(m - mn) + s2 * __expf(m2 - mn);
+  m = mn;
+}
+
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                            const int32_t* __restrict__ rows, const int64_t* __restrict__ tokens,
+                                                            float* __restrict__ row_lse, float* __restrict__ row_loss) {
+  __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
+  const int r = blockIdx.x;
+  const long long pos = rows[r];
+  const float* z = logits + pos * ld;
+  float m = -INFINITY, s = 0.f;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  int start = 0;
+  if (vec) {
+    const int nv = V >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    for (int i = threadIdx.x; i < nv; i += CE_THREADS) {
+      const float4 v = __ldg(z4 + i);
+      const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      const float mn = fmaxf(m, mx);
+      s = s * __expf(m - mn) + __expf(v.x - mn) + __expf(v.y - mn) + __expf(v.z - mn) + __expf(v.w - mn);
+      m = mn;
+    }
+    start = nv << 2;
+  }
+  for (int i = start + threadIdx.x; i < V; i += CE_THREADS) {
+    const float v = z[i];
+    const float mn = fmaxf(m, v);
+    s = s * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    online_merge(m, s, m2, s2);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < CE_THREADS / 32; ++w) online_merge(m, s, sm[w], ss[w]);
+    const float lse = m + logf(s);
+    const long long tgt = tokens[pos + 1];
+    row_lse[r] = lse;
+    row_loss[r] = (tgt >= 0 && tgt < V) ? lse - z[tgt] : 0.f;
+  }
+}
+
+// deterministic mean of row_loss
+__global__ void __launch_bounds__(1024) ce_mean_kernel(const float* __restrict__ row_loss, int n, float* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)row_loss[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *loss = (float)(t / (double)n);
+  }
+}
+
+__global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                            const int32_t* __restrict__ rows, int n_rows,
+                                                            const int64_t* __restrict__ tokens, const float* __restrict__ row_lse,
+                                                            const float* __restrict__ gscale, bf16* __restrict__ dlogits, long long ldd,
+                                                            int compact) {
+  const int r = blockIdx.x;
+  const long long pos = rows[r];
+  const float* z = logits + pos * ld;
+  bf16* dz = dlogits + (compact ? (long long)r : pos) * ldd;
+  const float lse = row_lse[r];
+  const float g = __ldg(gscale) / (float)n_rows;
+  const int tgt = (int)tokens[pos + 1];
+  const bool vec = ((ld & 3) == 0) && ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dlogits) & 7) == 0);
+  int start = 0;
+  if (vec) {
+    const int nv = V >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    uint2* d2 = reinterpret_cast<uint2*>(dz);
+    for (int i = threadIdx.x; i < nv; i += CE_THREADS) {
+      const float4 v = __ldg(z4 + i);
+      const int c = i << 2;
+      const float p0 = (__expf(v.x - lse) - (c == tgt ? 1.f : 0.f)) * g;
+      const float p1 = (__expf(v.y - lse) - (c + 1 == tgt ? 1.f : 0.f)) * g;
+      const float p2 = (__expf(v.z - lse) - (c + 2 == tgt ? 1.f : 0.f)) * g;
+      const float p3 = (__expf(v.w - lse) - (c + 3 == tgt ? 1.f : 0.f)) * g;
+      d2[i] = make_uint2(pack_bf16x2(p0, p1), pack_bf16x2(p2, p3));
+    }
+    start = nv << 2;
+  }
+  for (int i = start + threadIdx.x; i < V; i += CE_THREADS)
+    dz[i] = __float2bfloat16_rn((__expf(z[i] - lse) - (i == tgt ? 1.f : 0.f)) * g);
+}
+
+}  // namespace neko
+
+extern "C" {
+
+int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
+                       float* row_lse, float* row_loss, float* loss, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(logits && rows && tokens && row_lse && row_loss && loss, "masked_ce_fwd: null pointer");
+  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V, "masked_ce_fwd: bad sizes (V=%d n_rows=%d)", V, n_rows);
+  ce_fwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, tokens, row_lse, row_loss);
+  NEKO_LAUNCH_CHECK("ce_fwd_kernel");
+  ce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_rows, loss);
+  NEKO_LAUNCH_CHECK("ce_mean_kernel");
+  return NEKO_OK;
+}
+
+int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
+                       const float* row_lse, const float* gscale, uint16_t* dlogits, int64_t ld_dlogits, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(logits && rows && tokens && row_lse && gscale && dlogits, "masked_ce_bwd: null pointer");
+  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V && (ld_dlogits >= V || -ld_dlogits >= V), "masked_ce_bwd: bad sizes");
+  // a negative ld_dlogits selects the compact layout: row r of dlogits <- rows[r]
+  const int compact = ld_dlogits < 0 ? 1 : 0;
+  const long long ldd = compact ? -ld_dlogits : ld_dlogits;
+  ce_bwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, n_rows, tokens, row_lse, gscale,
+                                                             reinterpret_cast<bf16*>(dlogits), ldd, compact);
+  NEKO_LAUNCH_CHECK("ce_bwd_kernel");
+  return NEKO_OK;
+}
+
+}  // extern "C"

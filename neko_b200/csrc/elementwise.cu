@@ -1,0 +1,135 @@
+// Memory-bound helpers around the GEMMs: dtype cast, bias-gradient column sums, row gather/scatter.
+#include "common.cuh"
+
+namespace neko {
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long nv = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  uint2* d2 = reinterpret_cast<uint2*>(dst);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 v = __ldg(s4 + i);
+    d2[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// out[n] += sum over a row chunk of X[m, n].  Block = 32 x 8 threads, each thread owns 2 adjacent columns.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, long long ld, int M, int N, int rows_per_cta,
+                                                          float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + tx * 2;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float a0 = 0.f, a1 = 0.f;
+  if (col + 1 < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(X + (size_t)r * ld + col));
+      a0 += v.x; a1 += v.y;
+    }
+  } else if (col < N) {
+    for (int r = r0 + ty; r < r1; r += 8) a0 += __bfloat162float(X[(size_t)r * ld + col]);
+  }
+  red[ty][tx * 2] = a0;
+  red[ty][tx * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const bf16* __restrict__ src, long long ld_src, const int32_t* __restrict__ rows,
+                                                               int n_rows, int n, bf16* __restrict__ dst, long long ld_dst) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const bf16* s = src + (size_t)rows[w] * ld_src;
+  bf16* d = dst + (size_t)w * ld_dst;
+  if ((n & 7) == 0 && (ld_src & 7) == 0 && (ld_dst & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (int i = lane; i < (n >> 3); i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < n; i += 32) d[i] = s[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_rows_add_kernel(const bf16* __restrict__ src, long long ld_src, const int32_t* __restrict__ rows,
+                                                               int n_rows, int n, float* __restrict__ dst, long long ld_dst) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const bf16* s = src + (size_t)w * ld_src;
+  float* d = dst + (size_t)rows[w] * ld_dst;  // rows are unique: plain read-modify-write
+  for (int i = lane; i < n; i += 32) d[i] += __bfloat162float(s[i]);
+}
+
+}  // namespace neko
+
+extern "C" {
+
+int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(src && dst && n >= 0, "cast: bad arguments");
+  if (n == 0) return NEKO_OK;
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cast: misaligned buffers");
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  NEKO_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  return NEKO_OK;
+}
+
+int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, int accumulate, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(X && out && M > 0 && N > 0 && ld >= N, "colsum: bad arguments");
+  NEKO_REQUIRE(ld % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 3) == 0, "colsum: X must be 4-byte aligned with an even pitch");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, as_stream(stream));
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(colsum)");
+  }
+  const int col_blocks = (N + 63) / 64;
+  int row_chunks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+  if (row_chunks > (M + 63) / 64) row_chunks = (M + 63) / 64;
+  if (row_chunks < 1) row_chunks = 1;
+  const int rows_per_cta = (M + row_chunks - 1) / row_chunks;
+  dim3 grid(col_blocks, (M + rows_per_cta - 1) / rows_per_cta);
+  colsum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(X), ld, M, N, rows_per_cta, out);
+  NEKO_LAUNCH_CHECK("colsum_bf16_kernel");
+  return NEKO_OK;
+}
+
+int neko_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* rows, int n_rows, int n, uint16_t* dst,
+                          int64_t ld_dst, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(src && rows && dst && n > 0 && n_rows >= 0, "gather_rows: bad arguments");
+  if (n_rows == 0) return NEKO_OK;
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "gather_rows: misaligned");
+  const long long blocks = ((long long)n_rows * 32 + 255) / 256;
+  gather_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows, n,
+                                                                            reinterpret_cast<bf16*>(dst), ld_dst);
+  NEKO_LAUNCH_CHECK("gather_rows_bf16_kernel");
+  return NEKO_OK;
+}
+
+int neko_scatter_rows_add_f32(const uint16_t* src_bf16, int64_t ld_src, const int32_t* rows, int n_rows, int n, float* dst,
+                              int64_t ld_dst, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(src_bf16 && rows && dst && n > 0 && n_rows >= 0, "scatter_rows_add: bad arguments");
+  if (n_rows == 0) return NEKO_OK;
+  const long long blocks = ((long long)n_rows * 32 + 255) / 256;
+  scatter_rows_add_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src_bf16), ld_src, rows, n_rows, n, dst, ld_dst);
+  NEKO_LAUNCH_CHECK("scatter_rows_add_kernel");
+  return NEKO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,529 @@
+// Dense bf16 GEMM on the 5th-generation tensor cores: C[M,N] = epilogue(sum_k A[m,k] * B[n,k]).
+//
+// Replaces every dense contraction of the decoder and its autograd: HF Conv1D addmm
+// (trajectory_gpt2.py:222,253,274,277), predict_token (gato_policy.py:172),
+// post_embedding_projection (embeddings.py:53), plus dgrad / wgrad of each.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A and B into a
+//               STAGES-deep shared-memory ring, completion on mbarriers (full[]).
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16 per instruction)
+//               with the fp32 accumulator in TMEM; tcgen05.commit releases ring slots (empty[]) and
+//               publishes finished accumulators (tmem_full[]).  Two accumulator stages in TMEM so the
+//               epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time (each warp owns its 32-lane TMEM quarter),
+//               fused bias / GELU / residual / GELU' and 128-bit global stores.
+// Operands may be K-major or MN-major (UMMA descriptor major bits), so forward (x @ W[in,out]), dgrad and
+// wgrad all run from the tensors as they lie in HBM -- no transposed copies.
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace neko {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+struct GemmParams {
+  int M, N, K;
+  int BN;          // 128 or 256
+  int stages;
+  int a_mn, b_mn;  // operand majors
+  int epi;
+  int accumulate;
+  void* C;
+  long long ldc;
+  void* C2;
+  long long ldc2;
+  const float* bias;
+  const void* aux;
+  long long ld_aux;
+  int vec_ok;      // all epilogue pointers / leading dimensions allow 16-byte accesses
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version bit).  Offsets in bytes.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue on one 32-column chunk held by one thread (row = its TMEM lane)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v)[32], long long row, int col0) {
+  const int ncols = min(32, p.N - col0);
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (p.bias) {
+    if (ncols == 32 && p.vec_ok) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) f[i] += __ldg(p.bias + col0 + i);
+    }
+  }
+  const bool fast = (ncols == 32) && p.vec_ok;
+  switch (p.epi) {
+    case NEKO_EPI_BF16:
+    case NEKO_EPI_GELU_BF16:
+    case NEKO_EPI_DGELU_BF16: {
+      bf16* c = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col0;
+      if (p.epi == NEKO_EPI_DGELU_BF16) {
+        const bf16* a = reinterpret_cast<const bf16*>(p.aux) + row * p.ld_aux + col0;
+        if (fast) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(a);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = a4[i];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 pre = unpack_bf16x2(w[j]);
+              f[8 * i + 2 * j] *= gelu_erf_grad(pre.x);
+              f[8 * i + 2 * j + 1] *= gelu_erf_grad(pre.y);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) f[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+        }
+      }
+      if (fast) {
+        uint4* c4 = reinterpret_cast<uint4*>(c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                             pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) c[i] = __float2bfloat16_rn(f[i]);
+      }
+      if (p.epi == NEKO_EPI_GELU_BF16) {
+        bf16* c2 = reinterpret_cast<bf16*>(p.C2) + row * p.ldc2 + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        if (fast) {
+          uint4* c4 = reinterpret_cast<uint4*>(c2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                               pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) c2[i] = __float2bfloat16_rn(f[i]);
+        }
+      }
+      break;
+    }
+    default: {  // fp32 outputs
+      float* c = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+      const float* add = nullptr;
+      if (p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16)
+        add = reinterpret_cast<const float*>(p.aux) + row * p.ld_aux + col0;
+      else if (p.accumulate)
+        add = c;
+      if (add) {  // read everything before the (possibly aliasing) stores below
+        if (fast) {
+          const float4* a4 = reinterpret_cast<const float4*>(add);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = a4[i];
+            f[4 * i] += a.x; f[4 * i + 1] += a.y; f[4 * i + 2] += a.z; f[4 * i + 3] += a.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) f[i] += add[i];
+        }
+      }
+      if (fast) {
+        float4* c4 = reinterpret_cast<float4*>(c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) c[i] = f[i];
+      }
+      if (p.epi == NEKO_EPI_RESID_F32_BF16) {
+        bf16* c2 = reinterpret_cast<bf16*>(p.C2) + row * p.ldc2 + col0;
+        if (fast) {
+          uint4* c4 = reinterpret_cast<uint4*>(c2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                               pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) c2[i] = __float2bfloat16_rn(f[i]);
+        }
+      }
+      break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  const int stages = p.stages;
+  const uint32_t a_bytes = BM * BK * 2;
+  const uint32_t b_bytes = (uint32_t)BN * BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base address
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * stages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = 2u * BN;  // 256 or 512: a power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const long long tiles = (long long)m_blocks * n_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (int)(t % m_blocks) * BM;
+        const int n0 = (int)(t / m_blocks) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          mbar_expect_tx(full_bar(stage), stage_bytes);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+          } else {
+            for (int g = 0; g < BM / 64; ++g)                  // boxes {64 m, 64 k}
+              tma_load_2d(sa + g * (BK * 128), &map_a, full_bar(stage), m0 + g * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);  // box {64 k, BN n}
+          } else {
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_2d(sb + g * (BK * 128), &map_b, full_bar(stage), n0 + g * 64, k0);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: fp32 accumulate, bf16 x bf16, M=128, N=BN, operand majors
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: step 16 elements = 32 bytes inside the 128-byte swizzle row.
+            // MN-major: step 16 k-rows = two 8-row swizzle atoms = 2048 bytes.
+            const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 2048, BK * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // ring slot free once these MMAs have read it
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (int)(t % m_blocks) * BM;
+      const int n0 = (int)(t / m_blocks) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(taddr + (uint32_t)(c * 32), v);
+        if (row < p.M) epilogue_chunk(p, v, row, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point fetched at run time -- no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  unsigned long long inner, outer, ld;
+  unsigned box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.outer; h = h * 1000003u ^ k.ld;
+    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer;
+    return h;
+  }
+};
+
+// 2-D bf16 tensor [outer, inner] (inner contiguous, row pitch ld elements), box {box_inner, box_outer}.
+static int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner, unsigned long long outer, unsigned long long ld,
+                    unsigned box_inner, unsigned box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return NEKO_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return NEKO_ECUDA; }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {ld * 2ull};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr, inner, outer, ld, box_inner, box_outer);
+    return NEKO_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return NEKO_OK;
+}
+
+}  // namespace neko
+
+extern "C" int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t lda, int a_mn, const uint16_t* B, int64_t ldb,
+                              int b_mn, int epilogue, void* C, int64_t ldc, void* C2, int64_t ldc2, const float* bias,
+                              const void* aux, int64_t ld_aux, int accumulate, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
+  NEKO_REQUIRE(A && B && C, "gemm: null operand");
+  NEKO_REQUIRE(epilogue >= NEKO_EPI_BF16 && epilogue <= NEKO_EPI_RESID_F32_BF16, "gemm: unknown epilogue %d", epilogue);
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "gemm: operands must be 16-byte aligned");
+  NEKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements (TMA 16-byte pitch), got %lld %lld", (long long)lda, (long long)ldb);
+  NEKO_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm: leading dimension smaller than the row length");
+  if (epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_RESID_F32_BF16) NEKO_REQUIRE(C2 != nullptr, "gemm: epilogue %d needs C2", epilogue);
+  if (epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_RESID_F32_BF16 || epilogue == NEKO_EPI_DGELU_BF16)
+    NEKO_REQUIRE(aux != nullptr, "gemm: epilogue %d needs aux", epilogue);
+  NEKO_REQUIRE(!accumulate || epilogue == NEKO_EPI_F32, "gemm: accumulate is only defined for NEKO_EPI_F32");
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  p.epi = epilogue; p.accumulate = accumulate;
+  p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  // wide tiles when there are enough of them to fill the machine
+  const int sms = sm_count();
+  // tile width: fewest (waves x tile time); the narrow tile pays ~15% more operand traffic per flop
+  const long long mb_ = (M + BM - 1) / BM;
+  const long long tiles128 = mb_ * ((N + 127) / 128), tiles256 = mb_ * ((N + 255) / 256);
+  const double cost128 = 1.15 * (double)((tiles128 + sms - 1) / sms);
+  const double cost256 = 2.0 * (double)((tiles256 + sms - 1) / sms);
+  p.BN = (N > 128 && cost256 <= cost128) ? 256 : 128;
+  if (const char* force = getenv("NEKO_GEMM_BN")) { const int v = atoi(force); if (v == 128 || v == 256) p.BN = v; }
+  const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  p.stages = (SMEM_BUDGET - 1024 - 256) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  const bool out_bf16 = (epilogue == NEKO_EPI_BF16 || epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_DGELU_BF16);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool vec = al16(C) && (ldc % (out_bf16 ? 8 : 4) == 0);
+  if (C2) vec = vec && al16(C2) && (ldc2 % 8 == 0);
+  if (bias) vec = vec && al16(bias);
+  if (aux) vec = vec && al16(aux) && (ld_aux % (epilogue == NEKO_EPI_DGELU_BF16 ? 8 : 4) == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM);
+  else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK);
+  if (rc != NEKO_OK) return rc;
+  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN);
+  else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK);
+  if (rc != NEKO_OK) return rc;
+
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
+    attr_set = true;
+  }
+  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, p);
+  NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return NEKO_OK;
+}

@@ -1,0 +1,194 @@
+// LayerNorm forward / backward for the decoder (ln_1, ln_2, ln_f; trajectory_gpt2.py:323,353,779).
+//
+// Forward reads the fp32 residual stream and emits the bf16 GEMM operand plus per-row mean / rstd.
+// Backward fuses the residual-gradient add: dx_resid += LN'(dy), optionally emitting the bf16 copy
+// the next dgrad/wgrad GEMM consumes.  HBM-bound; one warp per row, 128-bit accesses, row kept in
+// registers (d <= 2048).
+#include "common.cuh"
+
+namespace neko {
+
+constexpr int LN_MAX_D = 2048;  // NV (float4 per lane) is a template parameter: 1,2,4,6,8,16
+
+template <int LN_MAX_VEC>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int N, int d, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int nv = d >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * d);
+  float4 v[LN_MAX_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = lane + k * 32;
+    if (i < nv) {
+      v[k] = x4[i];
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = lane + k * 32;
+    if (i < nv) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+      sq += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* y2 = reinterpret_cast<uint2*>(y + (size_t)row * d);
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = lane + k * 32;
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i), bb = __ldg(b4 + i);
+      uint2 o;
+      o.x = pack_bf16x2((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+      o.y = pack_bf16x2((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+      y2[i] = o;
+    }
+  }
+}
+
+// Each CTA owns `rows_per_cta` consecutive rows; warps stride over them.  dgamma / dbeta partials are
+// kept per lane in registers, reduced across the CTA's warps through shared memory, then one
+// atomicAdd per column per CTA.
+template <int LN_MAX_VEC>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ dx_resid,
+                                                            bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int N, int d, int rows_per_cta) {
+  extern __shared__ float smem[];  // [2][d] accumulators
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nv = d >> 2;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(N, row0 + rows_per_cta);
+  for (int row = row0 + wid; row < row1; row += nwarps) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    const uint2* dy2 = reinterpret_cast<const uint2*>(dy + (size_t)row * d);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAX_VEC], gy[LN_MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+      const int i = lane + k * 32;
+      if (i < nv) {
+        const float4 xv = x4[i];
+        const uint2 dv = dy2[i];
+        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+        const float4 g = __ldg(g4 + i);
+        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        ab[k].x += d01.x; ab[k].y += d01.y; ab[k].z += d23.x; ab[k].w += d23.y;
+        ag[k].x += d01.x * xh[k].x; ag[k].y += d01.y * xh[k].y; ag[k].z += d23.x * xh[k].z; ag[k].w += d23.y * xh[k].w;
+        gy[k] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
+        s1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
+        s2 += (gy[k].x * xh[k].x + gy[k].y * xh[k].y) + (gy[k].z * xh[k].z + gy[k].w * xh[k].w);
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+    float4* r4 = reinterpret_cast<float4*>(dx_resid + (size_t)row * d);
+    uint2* o2 = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * d) : nullptr;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+      const int i = lane + k * 32;
+      if (i < nv) {
+        float4 r = r4[i];
+        r.x += rs * (gy[k].x - s1 - xh[k].x * s2);
+        r.y += rs * (gy[k].y - s1 - xh[k].y * s2);
+        r.z += rs * (gy[k].z - s1 - xh[k].z * s2);
+        r.w += rs * (gy[k].w - s1 - xh[k].w * s2);
+        r4[i] = r;
+        if (o2) {
+          uint2 o;
+          o.x = pack_bf16x2(r.x, r.y);
+          o.y = pack_bf16x2(r.z, r.w);
+          o2[i] = o;
+        }
+      }
+    }
+  }
+  // CTA-level reduction of the affine gradients
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = lane + k * 32;
+    if (i < nv) {
+      float* sg = smem + 4 * i;
+      float* sb = smem + d + 4 * i;
+      atomicAdd(sg + 0, ag[k].x); atomicAdd(sg + 1, ag[k].y); atomicAdd(sg + 2, ag[k].z); atomicAdd(sg + 3, ag[k].w);
+      atomicAdd(sb + 0, ab[k].x); atomicAdd(sb + 1, ab[k].y); atomicAdd(sb + 2, ab[k].z); atomicAdd(sb + 3, ab[k].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, smem[i]);
+    atomicAdd(dbeta + i, smem[d + i]);
+  }
+}
+
+}  // namespace neko
+
+extern "C" {
+
+int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_bf16, float* mean,
+                       float* rstd, int N, int d, float eps, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(x && gamma && beta && y_bf16 && mean && rstd, "layernorm_fwd: null pointer");
+  NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_fwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
+  const int threads = 256;
+  const long long blocks = ((long long)N * 32 + threads - 1) / threads;
+#define NEKO_LN_FWD(NV) layernorm_fwd_kernel<NV><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), mean, rstd, N, d, eps)
+  const int need = (d / 4 + 31) / 32;
+  if (need <= 1) NEKO_LN_FWD(1); else if (need <= 2) NEKO_LN_FWD(2); else if (need <= 4) NEKO_LN_FWD(4);
+  else if (need <= 6) NEKO_LN_FWD(6); else if (need <= 8) NEKO_LN_FWD(8); else NEKO_LN_FWD(16);
+#undef NEKO_LN_FWD
+  NEKO_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return NEKO_OK;
+}
+
+int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       float* dx_resid, uint16_t* dx_bf16, float* dgamma, float* dbeta, int N, int d, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(dy_bf16 && x && gamma && mean && rstd && dx_resid && dgamma && dbeta, "layernorm_bwd: null pointer");
+  NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_bwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
+  const int threads = 256;
+  // ~4 CTAs per SM, each a contiguous row range
+  int ctas = sm_count() * 4;
+  int rows_per_cta = (N + ctas - 1) / ctas;
+  if (rows_per_cta < 8) rows_per_cta = 8;
+  ctas = (N + rows_per_cta - 1) / rows_per_cta;
+  const size_t smem = 2 * (size_t)d * sizeof(float);
+#define NEKO_LN_BWD(NV) layernorm_bwd_kernel<NV><<<ctas, threads, smem, as_stream(stream)>>>(reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid, reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, N, d, rows_per_cta)
+  const int need = (d / 4 + 31) / 32;
+  if (need <= 1) NEKO_LN_BWD(1); else if (need <= 2) NEKO_LN_BWD(2); else if (need <= 4) NEKO_LN_BWD(4);
+  else if (need <= 6) NEKO_LN_BWD(6); else if (need <= 8) NEKO_LN_BWD(8); else NEKO_LN_BWD(16);
+#undef NEKO_LN_BWD
+  NEKO_LAUNCH_CHECK("layernorm_bwd_kernel");
+  return NEKO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Thin torch-tensor wrappers over the C ABI (include/neko_b200.h).
+
+PyTorch is used only for device memory and streams; every computation is a call into
+libneko_b200.so.  All functions enqueue on the current CUDA stream and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_RESID_F32_BF16,  # noqa: F401
+                   SampleDesc, TokParams, _p, check, load, stream_ptr)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.NekoError("neko_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
+         out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, accumulate: bool = False, M: Optional[int] = None,
+         N: Optional[int] = None, K: Optional[int] = None) -> torch.Tensor:
+    """C[M,N] = epilogue(sum_k A[m,k] B[n,k]).
+
+    a: bf16 [M,K] (a_mn=False) or [K,M] (a_mn=True); b: bf16 [N,K] or [K,N]; rows may be strided
+    (stride(0) is the leading dimension)."""
+    _cuda(a, b, out, out2, bias, aux)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if K is None:
+        K = a.shape[0] if a_mn else a.shape[1]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    bf16_out = epilogue in (EPI_BF16, EPI_GELU_BF16, EPI_DGELU_BF16)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    if epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16) and out2 is None:
+        out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    assert out.stride(1) == 1
+    check(load().neko_gemm_bf16(
+        C.c_int(M), C.c_int(N), C.c_int(K), _p(a), C.c_int64(a.stride(0)), C.c_int(int(a_mn)),
+        _p(b), C.c_int64(b.stride(0)), C.c_int(int(b_mn)), C.c_int(epilogue), _p(out), C.c_int64(out.stride(0)),
+        _p(out2), C.c_int64(out2.stride(0) if out2 is not None else 0), _p(bias), _p(aux),
+        C.c_int64(aux.stride(0) if aux is not None else 0), C.c_int(int(accumulate)), stream_ptr()), "neko_gemm_bf16")
+    if out2 is not None and epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16):
+        return out, out2
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, y=None, mean=None, rstd=None):
+    _cuda(x, gamma, beta)
+    N, d = x.shape
+    if y is None:
+        y = torch.empty(N, d, device=x.device, dtype=torch.bfloat16)
+    if mean is None:
+        mean = torch.empty(N, device=x.device, dtype=torch.float32)
+    if rstd is None:
+        rstd = torch.empty(N, device=x.device, dtype=torch.float32)
+    check(load().neko_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), C.c_int(N), C.c_int(d),
+                                    C.c_float(eps), stream_ptr()), "neko_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf16=None):
+    N, d = x.shape
+    check(load().neko_layernorm_bwd(_p(dy_bf16), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx_bf16),
+                                    _p(dgamma), _p(dbeta), C.c_int(N), C.c_int(d), stream_ptr()), "neko_layernorm_bwd")
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid: Optional[int] = None, out=None, lse=None):
+    B, S, three_d = qkv.shape
+    d = three_d // 3
+    dh = d // H
+    if out is None:
+        out = torch.empty(B, S, d, device=qkv.device, dtype=torch.bfloat16)
+    if lse is None:
+        lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    check(load().neko_attention_fwd(_p(qkv), _p(first_valid), _p(out), _p(lse), C.c_int(B), C.c_int(S),
+                                    C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh), stream_ptr()),
+          "neko_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[int] = None, dqkv=None, delta=None):
+    B, S, three_d = qkv.shape
+    dh = three_d // 3 // H
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta is None:
+        delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    check(load().neko_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(first_valid), _p(dqkv), _p(delta), C.c_int(B),
+                                    C.c_int(S), C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh),
+                                    stream_ptr()), "neko_attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------
+# masked cross entropy
+# ------------------------------------------------------------------------------------------
+def masked_ce_fwd(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torch.Tensor):
+    """logits fp32 [N, ld]; rows int32 [n]; tokens int64 flat [N]."""
+    n = rows.numel()
+    row_lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+    row_loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(load().neko_masked_ce_fwd(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens),
+                                    _p(row_lse), _p(row_loss), _p(loss), stream_ptr()), "neko_masked_ce_fwd")
+    return loss, row_lse, row_loss
+
+
+def masked_ce_bwd(logits, V, rows, tokens, row_lse, gscale, dlogits, compact: bool = False):
+    n = rows.numel()
+    ld = dlogits.stride(-2)
+    check(load().neko_masked_ce_bwd(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens),
+                                    _p(row_lse), _p(gscale), _p(dlogits), C.c_int64(-ld if compact else ld), stream_ptr()),
+          "neko_masked_ce_bwd")
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    check(load().neko_cast_f32_to_bf16(_p(src), _p(dst), C.c_int64(src.numel()), stream_ptr()), "neko_cast_f32_to_bf16")
+    return dst
+
+
+def colsum(x_bf16: torch.Tensor, out: torch.Tensor, accumulate: bool = False, M: Optional[int] = None, N: Optional[int] = None):
+    M = x_bf16.shape[0] if M is None else M
+    N = x_bf16.shape[1] if N is None else N
+    check(load().neko_colsum_bf16(_p(x_bf16), C.c_int64(x_bf16.stride(0)), C.c_int(M), C.c_int(N), _p(out),
+                                  C.c_int(int(accumulate)), stream_ptr()), "neko_colsum_bf16")
+    return out
+
+
+def gather_rows(src_bf16, rows, n: int, dst):
+    check(load().neko_gather_rows_bf16(_p(src_bf16), C.c_int64(src_bf16.stride(0)), _p(rows), C.c_int(rows.numel()), C.c_int(n),
+                                       _p(dst), C.c_int64(dst.stride(0)), stream_ptr()), "neko_gather_rows_bf16")
+    return dst
+
+
+def scatter_rows_add(src_bf16, rows, n: int, dst_f32):
+    check(load().neko_scatter_rows_add_f32(_p(src_bf16), C.c_int64(src_bf16.stride(0)), _p(rows), C.c_int(rows.numel()),
+                                           C.c_int(n), _p(dst_f32), C.c_int64(dst_f32.stride(0)), stream_ptr()),
+          "neko_scatter_rows_add_f32")
+    return dst_f32
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor):
+    check(load().neko_sumsq_f32(_p(x), C.c_int64(x.numel()), _p(out), stream_ptr()), "neko_sumsq_f32")
+    return out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq=None, max_norm=0.0,
+               grad_div=1.0):
+    check(load().neko_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), C.c_int64(param.numel()), C.c_float(lr),
+                                 C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int(step),
+                                 _p(grad_sumsq), C.c_float(max_norm), C.c_float(grad_div), stream_ptr()), "neko_adamw_step")

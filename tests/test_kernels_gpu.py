@@ -1,0 +1,267 @@
+"""Kernel-level parity: every C-ABI entry point against a plain torch fp32 restatement of the same op,
+on the same seeded inputs.  GPU only (-m gpu)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from neko_b200 import _lib, ops as _ops
+    _lib.require_device()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 128, 256), (256, 384, 768), (200, 72, 104), (1000, 200, 72), (130, 520, 1032),
+    (7680, 2304, 768), (7680, 768, 3072), (1024, 768, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_layouts(ops, M, N, K, a_mn, b_mn):
+    # leading dimensions must be multiples of 8 elements: pad the storage, slice the logical view
+    def pad8(n):
+        return (n + 7) // 8 * 8
+    a_log = _rand((M, K), 1, 0.5)
+    b_log = _rand((N, K), 2, 0.5)
+    if a_mn:
+        a_store = torch.zeros(K, pad8(M), device="cuda", dtype=torch.bfloat16)
+        a_store[:, :M] = a_log.t().to(torch.bfloat16)
+        a = a_store[:, :M]
+    else:
+        a_store = torch.zeros(M, pad8(K), device="cuda", dtype=torch.bfloat16)
+        a_store[:, :K] = a_log.to(torch.bfloat16)
+        a = a_store[:, :K]
+    if b_mn:
+        b_store = torch.zeros(K, pad8(N), device="cuda", dtype=torch.bfloat16)
+        b_store[:, :N] = b_log.t().to(torch.bfloat16)
+        b = b_store[:, :N]
+    else:
+        b_store = torch.zeros(N, pad8(K), device="cuda", dtype=torch.bfloat16)
+        b_store[:, :K] = b_log.to(torch.bfloat16)
+        b = b_store[:, :K]
+    ref = a_log.to(torch.bfloat16).float() @ b_log.to(torch.bfloat16).float().t()
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, epilogue=ops.EPI_F32, M=M, N=N, K=K)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    tol = 2e-3 * math.sqrt(K / 64) + 1e-4
+    assert err < tol, f"max err {err} (tol {tol})"
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 384, 256, 192
+    a = _rand((M, K), 3, 0.5, torch.bfloat16)
+    b = _rand((N, K), 4, 0.5, torch.bfloat16)
+    bias = _rand((N,), 5)
+    resid = _rand((M, N), 6)
+    pre = _rand((M, N), 7, 1.0, torch.bfloat16)
+    acc = a.float() @ b.float().t()
+
+    out = ops.gemm(a, b, epilogue=ops.EPI_BF16, bias=bias)
+    assert (out.float() - (acc + bias)).abs().max().item() < 0.08
+    out = ops.gemm(a, b, epilogue=ops.EPI_BF16)
+    assert (out.float() - acc).abs().max().item() < 0.08
+
+    out = ops.gemm(a, b, epilogue=ops.EPI_F32, bias=bias)
+    assert (out - (acc + bias)).abs().max().item() < 2e-3
+    base = resid.clone()
+    out = ops.gemm(a, b, epilogue=ops.EPI_F32, out=base, accumulate=True)
+    assert (out - (acc + resid)).abs().max().item() < 2e-3
+
+    pre_o, act_o = ops.gemm(a, b, epilogue=ops.EPI_GELU_BF16, bias=bias)
+    assert (pre_o.float() - (acc + bias)).abs().max().item() < 0.08
+    assert (act_o.float() - torch.nn.functional.gelu(acc + bias)).abs().max().item() < 0.08
+
+    x = resid.clone()
+    out = ops.gemm(a, b, epilogue=ops.EPI_RESID_F32, bias=bias, aux=x, out=x)  # in place on the residual stream
+    assert (out - (acc + bias + resid)).abs().max().item() < 2e-3
+
+    x = resid.clone()
+    out, out_bf = ops.gemm(a, b, epilogue=ops.EPI_RESID_F32_BF16, bias=bias, aux=x, out=x)
+    assert (out - (acc + bias + resid)).abs().max().item() < 2e-3
+    assert (out_bf.float() - out).abs().max().item() < 0.08
+
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).sum().backward()
+    out = ops.gemm(a, b, epilogue=ops.EPI_DGELU_BF16, aux=pre)
+    assert (out.float() - acc * p.grad).abs().max().item() < 0.1
+
+
+def test_gemm_lm_head_shape(ops):
+    """K=768, N = 52305 rows of W padded to a 52352-column output (OOB rows of B zero-filled by TMA)."""
+    M, K, V, Vp = 256, 768, 52305, 52352
+    h = _rand((M, K), 8, 1.0, torch.bfloat16)
+    w = _rand((V, K), 9, 0.02, torch.bfloat16)
+    out = torch.full((M, Vp), float("nan"), device="cuda")
+    ops.gemm(h, w, epilogue=ops.EPI_F32, out=out, N=Vp)
+    ref = h.float() @ w.float().t()
+    assert (out[:, :V] - ref).abs().max().item() < 5e-3
+    assert (out[:, V:] == 0).all()
+    # dgrad through the head: dh = dlogits[M,Vp] @ W[V,K] with K-tail on the vocabulary
+    dl = torch.zeros(M, Vp, device="cuda", dtype=torch.bfloat16)
+    dl[:, :V] = _rand((M, V), 10, 0.01, torch.bfloat16)
+    dh = ops.gemm(dl, w, b_mn=True, epilogue=ops.EPI_F32, K=V, N=K)
+    ref = dl[:, :V].float() @ w.float()
+    assert (dh - ref).abs().max().item() < 5e-3
+    # wgrad: dW[V,K] = dlogits^T h
+    dw = ops.gemm(dl, h, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, M=V, N=K, K=M)
+    ref = dl[:, :V].float().t() @ h.float()
+    assert (dw - ref).abs().max().item() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,d", [(37, 32), (1000, 64), (513, 128), (2048, 768), (100, 1024), (64, 2048)])
+def test_layernorm(ops, N, d):
+    x = _rand((N, d), 11, 2.0) + 0.5
+    g = _rand((d,), 12, 0.2) + 1.0
+    b = _rand((d,), 13, 0.2)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5)
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5)
+    assert (y.float() - ref).abs().max().item() < 0.05
+    assert (mean - x.mean(-1)).abs().max().item() < 1e-5
+    dy = _rand((N, d), 14, 1.0, torch.bfloat16)
+    ref.backward(dy.float())
+    resid = _rand((N, d), 15)
+    dx = resid.clone()
+    dg = torch.zeros(d, device="cuda")
+    db = torch.zeros(d, device="cuda")
+    dx_bf = torch.empty(N, d, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, dx_bf)
+    assert (dx - (resid + xr.grad)).abs().max().item() < 2e-4
+    assert (dx_bf.float() - dx).abs().max().item() < 0.05
+    assert (dg - gr.grad).abs().max().item() < 2e-3 * math.sqrt(N)
+    assert (db - br.grad).abs().max().item() < 2e-3 * math.sqrt(N)
+
+
+# ---------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, first_valid, H, S_valid):
+    """Reference semantics (trajectory_gpt2.py:163-188 + 663-679) in fp32 with -1e4 fills."""
+    B, S, three_d = qkv.shape
+    d = three_d // 3
+    dh = d // H
+    q, k, v = qkv.float().split(d, dim=2)
+    q = q.reshape(B, S, H, dh).permute(0, 2, 1, 3)
+    k = k.reshape(B, S, H, dh).permute(0, 2, 3, 1)
+    v = v.reshape(B, S, H, dh).permute(0, 2, 1, 3)
+    pos = torch.arange(S, device=qkv.device)
+    mask = ((pos[None, :] >= first_valid[:, None]) & (pos[None, :] < S_valid)).float()
+    w = torch.matmul(q, k) / (float(dh) ** 0.5)
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool, device=qkv.device))[None, None]
+    w = torch.where(causal, w, torch.tensor(-1e4, device=qkv.device))
+    w = w + ((1.0 - mask) * -10000.0)[:, None, None, :]
+    p = torch.softmax(w, dim=-1)
+    return torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B, S, d), mask
+
+
+@pytest.mark.parametrize("B,S,H,dh,S_valid", [(2, 64, 2, 32, 64), (3, 100, 3, 32, 100), (2, 240, 24, 32, 240), (2, 130, 1, 128, 130),
+                                               (2, 96, 4, 16, 80), (2, 200, 2, 64, 200), (1, 494, 24, 32, 494)])
+def test_attention_fwd_bwd(ops, B, S, H, dh, S_valid):
+    d = H * dh
+    qkv = _rand((B, S, 3 * d), 21, 1.0, torch.bfloat16)
+    fv = torch.tensor([0, 17, 70][:B], dtype=torch.int32).clamp(max=S_valid - 1).cuda()
+    out, lse = ops.attention_fwd(qkv, fv, H, S_valid)
+    x = qkv.float().requires_grad_(True)
+    ref, mask = _attn_ref(x, fv, H, S_valid)
+    live = mask.bool()[:, :, None].expand(B, S, d)
+    err = ((out.float() - ref) * live).abs().max().item()
+    assert err < 0.03, err
+    assert (out.float() * (~live)).abs().max().item() == 0.0  # padded rows are zeros
+    dout = _rand((B, S, d), 22, 1.0, torch.bfloat16) * live
+    (ref * dout.float()).sum().backward()
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, fv, H, S_valid)
+    gref = x.grad
+    scale = gref.abs().max().item()
+    err = (dqkv.float() - gref).abs().max().item()
+    assert err < 0.03 * max(scale, 1.0), (err, scale)
+
+
+# ---------------------------------------------------------------------------------------------------
+# masked cross entropy
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,ld", [(2208, 2208), (52305, 52352), (1001, 1001)])
+def test_masked_ce(ops, V, ld):
+    B, S = 3, 40
+    N = B * S
+    store = torch.zeros(N, ld, device="cuda")
+    store[:, :V] = _rand((N, V), 31, 2.0)
+    tokens = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(5)).cuda()
+    g = torch.Generator().manual_seed(6)
+    sel = (torch.rand(B, S - 1, generator=g) < 0.3)
+    rows = (torch.arange(B)[:, None] * S + torch.arange(S - 1)[None, :])[sel].to(torch.int32).cuda()
+    loss, row_lse, row_loss = ops.masked_ce_fwd(store, V, rows, tokens.reshape(-1))
+    z = store[:, :V].clone().requires_grad_(True)
+    tgt = tokens.reshape(-1)[rows.long() + 1]
+    ref = torch.nn.functional.cross_entropy(z[rows.long()], tgt)
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    (ref * 0.5).backward()
+    gs = torch.tensor(0.5, device="cuda")
+    dl = torch.zeros(N, ld, device="cuda", dtype=torch.bfloat16)
+    ops.masked_ce_bwd(store, V, rows, tokens.reshape(-1), row_lse, gs, dl)
+    assert (dl[:, :V].float() - z.grad).abs().max().item() < 2e-3 * z.grad.abs().max().item() + 1e-6
+    dlc = torch.zeros(rows.numel(), ld, device="cuda", dtype=torch.bfloat16)
+    ops.masked_ce_bwd(store, V, rows, tokens.reshape(-1), row_lse, gs, dlc, compact=True)
+    assert torch.equal(dlc, dl[rows.long()])
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def test_cast_colsum_rows(ops):
+    x = _rand((1000, 777), 41)
+    xb = ops.cast_bf16(x.contiguous())
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    y = _rand((3000, 776), 42, 1.0, torch.bfloat16)
+    out = torch.zeros(776, device="cuda")
+    ops.colsum(y, out)
+    assert (out - y.float().sum(0)).abs().max().item() < 0.05
+    ops.colsum(y, out, accumulate=True)
+    assert (out - 2 * y.float().sum(0)).abs().max().item() < 0.1
+    rows = torch.randperm(3000)[:500].to(torch.int32).cuda()
+    g = torch.empty(500, 776, device="cuda", dtype=torch.bfloat16)
+    ops.gather_rows(y, rows, 776, g)
+    assert torch.equal(g, y[rows.long()])
+    dst = _rand((3000, 776), 43)
+    ref = dst.clone()
+    ref[rows.long()] += g.float()
+    ops.scatter_rows_add(g, rows, 776, dst)
+    assert (dst - ref).abs().max().item() < 1e-6
+
+
+def test_adamw_clip(ops):
+    n = 100_003
+    p = _rand((n,), 51)
+    g = _rand((n,), 52, 3.0)
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    for step in range(1, 4):
+        pr.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([pr], 1.0)
+        opt.step()
+        ss = torch.zeros((), device="cuda")
+        ops.sumsq(g, ss)
+        ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, ss, 1.0)
+    assert (p - pr.detach()).abs().max().item() < 1e-5
