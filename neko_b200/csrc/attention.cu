@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
         const int key = j0 + n * 8 + 2 * q;
-        if (key < lo || key > row_a) s[n][0] = -INFINITY;
-        if (key + 1 < lo || key + 1 > row_a) s[n][1] = -INFINITY;
-        if (key < lo || key > row_b) s[n][2] = -INFINITY;
-        if (key + 1 < lo || key + 1 > row_b) s[n][3] = -INFINITY;
+        if (key < lo || key > row_a || row_a >= S_valid) s[n][0] = -INFINITY;
+        if (key + 1 < lo || key + 1 > row_a || row_a >= S_valid) s[n][1] = -INFINITY;
+        if (key < lo || key > row_b || row_b >= S_valid) s[n][2] = -INFINITY;
+        if (key + 1 < lo || key + 1 > row_b || row_b >= S_valid) s[n][3] = -INFINITY;
         mx_a = fmaxf(mx_a, fmaxf(s[n][0], s[n][1]));
         mx_b = fmaxf(mx_b, fmaxf(s[n][2], s[n][3]));
       }

@@ -1,0 +1,238 @@
+"""Host-side batch plan for the fused tokenise/embed kernel.
+
+Turns the reference's list-of-dicts input (docstring of tokenize_input_dicts, gato_policy.py:196-244)
+into: one descriptor per sample (neko_sample_desc), one packed fp32 buffer (continuous obs/actions),
+one packed int32 buffer (text ids, discrete obs/actions), image groups, and -- because every mask is a
+function of the SHAPES only -- the loss-row list of gato_policy.py:177-185 without touching the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .._lib import SampleDesc
+
+
+@dataclass
+class ImageGroup:
+    """Samples whose frames share (H, W, dtype): one patch-embed launch."""
+    height: int
+    width: int
+    is_u8: bool
+    tensors: List[torch.Tensor] = field(default_factory=list)   # [T,3,H,W] each
+    sample_idx: List[int] = field(default_factory=list)
+    patch_off: List[int] = field(default_factory=list)           # first patch row of each sample
+    n_frames: int = 0
+
+
+@dataclass
+class BatchPlan:
+    B: int
+    seq_len: int            # S: longest sample
+    width: int              # S, or context_len with pad_seq
+    descs: np.ndarray       # structured bytes of B neko_sample_desc
+    fvals: List[torch.Tensor]
+    ivals: List[torch.Tensor]
+    n_f: int
+    n_i: int
+    first_valid: np.ndarray  # int32 [B] = seq_off
+    loss_rows: np.ndarray    # int32 [n_rows] flat positions b*width+s
+    n_valid_tokens: int
+    image_groups: List[ImageGroup]
+    n_patch_rows: int
+    precomputed_patch: List[Tuple[int, torch.Tensor]]  # (patch_off, image_embeddings [T,P,d])
+
+
+def _is_present(d: dict, k: str) -> bool:
+    return k in d and d[k] is not None
+
+
+def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad_seq: bool) -> BatchPlan:
+    B = len(inputs)
+    assert B > 0, "empty batch"
+    descs = (SampleDesc * B)()
+    fvals: List[torch.Tensor] = []
+    ivals: List[torch.Tensor] = []
+    n_f = n_i = 0
+    groups: List[ImageGroup] = []
+    pre_patch: List[Tuple[int, torch.Tensor]] = []
+    n_patch_rows = 0
+    lengths = []
+    tgt_patterns = []
+
+    def add_f(t: torch.Tensor) -> int:
+        nonlocal n_f
+        off = n_f
+        t = t.detach()
+        if t.dtype != torch.float32:
+            t = t.to(torch.float32)
+        fvals.append(t.reshape(-1))
+        n_f += t.numel()
+        return off
+
+    def add_i(t) -> int:
+        nonlocal n_i
+        off = n_i
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        t = t.detach()
+        if t.dtype != torch.int32:
+            t = t.to(torch.int32)
+        ivals.append(t.reshape(-1))
+        n_i += t.numel()
+        return off
+
+    for b, s in enumerate(inputs):
+        d = descs[b]
+        T: Optional[int] = None
+
+        def check_T(n: int):
+            nonlocal T
+            if T is None:
+                T = n
+            else:
+                assert T == n, "number of timesteps must be the same for all modalities"
+
+        if _is_present(s, "text"):
+            txt = s["text"]
+            if isinstance(txt, list):
+                # torch.Tensor(list) -> fp32 -> long in the reference (gato_policy.py:266-273)
+                txt = torch.tensor(txt, dtype=torch.float32).unsqueeze(0)
+            elif txt.dim() == 1:
+                txt = txt.unsqueeze(0)
+            T = int(txt.shape[0])
+            d.n_text = int(txt.shape[1])
+            d.text_off = add_i(txt.long())
+        if _is_present(s, "images") or _is_present(s, "image_embeddings"):
+            if _is_present(s, "image_embeddings"):
+                emb = s["image_embeddings"]
+                n_img, n_p = int(emb.shape[0]), int(emb.shape[1])
+                pre_patch.append((n_patch_rows, emb))
+            else:
+                im = s["images"]
+                assert im.dim() == 4 and im.shape[1] == 3, "images must be [T,3,H,W]"
+                h, w = int(im.shape[2]), int(im.shape[3])
+                assert h % patch_size == 0 and w % patch_size == 0, "Image dimensions must be divisible by patch size"
+                n_img, n_p = int(im.shape[0]), (h // patch_size) * (w // patch_size)
+                is_u8 = im.dtype == torch.uint8
+                if not is_u8 and im.dtype != torch.float32:
+                    im = im.to(torch.float32)
+                grp = next((g for g in groups if g.height == h and g.width == w and g.is_u8 == is_u8), None)
+                if grp is None:
+                    grp = ImageGroup(h, w, is_u8)
+                    groups.append(grp)
+                grp.tensors.append(im)
+                grp.sample_idx.append(b)
+                grp.patch_off.append(n_patch_rows)
+                grp.n_frames += n_img
+            check_T(n_img)
+            d.n_patches = n_p
+            d.patch_off = n_patch_rows
+            n_patch_rows += n_img * n_p
+        if _is_present(s, "continuous_obs"):
+            t = s["continuous_obs"]
+            check_T(int(t.shape[0]))
+            d.n_cobs = int(t.shape[1])
+            d.cobs_off = add_f(t)
+        if _is_present(s, "discrete_obs"):
+            t = s["discrete_obs"]
+            check_T(int(t.shape[0]))
+            d.n_dobs = int(t.shape[1])
+            d.dobs_off = add_i(t)
+        if _is_present(s, "continuous_actions"):
+            t = s["continuous_actions"]
+            check_T(int(t.shape[0]))
+            d.n_cact = int(t.shape[1])
+            d.cact_off = add_f(t)
+        if _is_present(s, "discrete_actions"):
+            t = s["discrete_actions"]
+            check_T(int(t.shape[0]))
+            d.n_dact = int(t.shape[1])
+            d.dact_off = add_i(t)
+        assert T is not None, "sample has no modality"
+        d.n_timesteps = T
+        n_obs = d.n_patches + d.n_text + d.n_cobs + d.n_dobs
+        tpt = n_obs + 1 + d.n_cact + d.n_dact
+        lengths.append(T * tpt)
+        # per-timestep target pattern (gato_policy.py:362-369): text and actions are targets
+        pat = np.zeros(tpt, dtype=np.uint8)
+        pat[d.n_patches:d.n_patches + d.n_text] = 1
+        pat[n_obs + 1:] = 1
+        tgt_patterns.append(np.tile(pat, T))
+
+    S = max(lengths)
+    width = context_len if (pad_seq and context_len > S) else S
+    first_valid = np.zeros(B, dtype=np.int32)
+    rows = []
+    for b in range(B):
+        off = S - lengths[b]
+        descs[b].seq_off = off
+        first_valid[b] = off
+        # loss row s: token s valid (s >= off) and target mask at s+1 set, s+1 < S
+        tgt = tgt_patterns[b]
+        sel = np.nonzero(tgt[1:])[0]           # local source positions 0..len-2
+        rows.append((b * width + off + sel).astype(np.int32))
+    loss_rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int32)
+    raw = np.frombuffer(C.string_at(C.addressof(descs), C.sizeof(descs)), dtype=np.uint8).copy()
+    return BatchPlan(B=B, seq_len=S, width=width, descs=raw, fvals=fvals, ivals=ivals, n_f=n_f, n_i=n_i,
+                     first_valid=first_valid, loss_rows=loss_rows, n_valid_tokens=int(sum(lengths)),
+                     image_groups=groups, n_patch_rows=n_patch_rows, precomputed_patch=pre_patch)
+
+
+class Stager:
+    """One pinned host buffer + one device buffer per batch: every small input (descriptors, scalars, ids,
+    loss rows) crosses PCIe in a single cudaMemcpyAsync."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._pinned: Optional[torch.Tensor] = None
+        self._dev: Optional[torch.Tensor] = None
+
+    def _ensure(self, nbytes: int):
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            cap = max(nbytes, 1 << 20)
+            cap = 1 << (cap - 1).bit_length()
+            self._pinned = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+
+    def upload(self, plan: BatchPlan):
+        """Returns device views: descs(u8), fvals(f32), ivals(i32), first_valid(i32), loss_rows(i32) and the
+        number of host->device bytes moved."""
+        def al(n):
+            return (n + 255) // 256 * 256
+        host_f = all(not t.is_cuda for t in plan.fvals)
+        host_i = all(not t.is_cuda for t in plan.ivals)
+        sizes = [plan.descs.nbytes, plan.n_f * 4 if host_f else 0, plan.n_i * 4 if host_i else 0,
+                 plan.first_valid.nbytes, plan.loss_rows.nbytes]
+        offs = np.cumsum([0] + [al(s) for s in sizes])
+        total = int(offs[-1])
+        self._ensure(total)
+        pin = self._pinned
+        pin[offs[0]:offs[0] + sizes[0]] = torch.from_numpy(plan.descs)
+        if host_f and plan.n_f:
+            torch.cat(plan.fvals, out=pin[offs[1]:offs[1] + sizes[1]].view(torch.float32))
+        if host_i and plan.n_i:
+            torch.cat(plan.ivals, out=pin[offs[2]:offs[2] + sizes[2]].view(torch.int32))
+        pin[offs[3]:offs[3] + sizes[3]] = torch.from_numpy(plan.first_valid.view(np.uint8))
+        if sizes[4]:
+            pin[offs[4]:offs[4] + sizes[4]] = torch.from_numpy(plan.loss_rows.view(np.uint8))
+        dev = self._dev
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        h2d = total
+
+        def view(i, dtype):
+            return dev[offs[i]:offs[i] + sizes[i]].view(dtype)
+        descs = dev[offs[0]:offs[0] + sizes[0]]
+        if host_f:
+            fv = view(1, torch.float32)
+        else:  # inputs already live on the device (the reference's ControlTask does this): gather there
+            fv = torch.cat([t.to(self.device) for t in plan.fvals]) if plan.n_f else dev[:0].view(torch.float32)
+        if host_i:
+            iv = view(2, torch.int32)
+        else:
+            iv = torch.cat([t.to(self.device) for t in plan.ivals]) if plan.n_i else dev[:0].view(torch.int32)
+        return descs, fv, iv, view(3, torch.int32), view(4, torch.int32), h2d
