@@ -105,6 +105,8 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
  * Dense GEMM on tcgen05 tensor cores (HF Conv1D addmm trajectory_gpt2.py:222,253,274,277;
  * predict_token gato_policy.py:172; post_embedding_projection embeddings.py:53; and their
  * autograd dgrad / wgrad).   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ).
+ * The operand buffers must cover the full (tile-padded is NOT required; TMA zero-fills past M/N/K) logical
+ * extents given by M, N, K.
  * a_mn / b_mn = 0: operand is K-major (row m / n is contiguous in k, leading dimension ld);
  *             = 1: operand is MN-major (stored [K, M] / [K, N] row-major, leading dimension ld).
  * ------------------------------------------------------------------------------------------- */
@@ -139,15 +141,16 @@ int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t*
  * Masked cross entropy (gato_policy.py:174-186).  rows int32 [n_rows]: flat source positions
  * b*S_width+s whose target is tokens[row+1]; loss = mean over rows (written to *loss).
  * ------------------------------------------------------------------------------------------- */
+#define NEKO_CE_LOGITS_COMPACT 1   /* logits row r (not rows[r]) holds position rows[r]            */
+#define NEKO_CE_DLOGITS_COMPACT 2  /* dlogits row r (not rows[r]) receives position rows[r]         */
 int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
-                       const int64_t* tokens, float* row_lse, float* row_loss, float* loss,
+                       const int64_t* tokens, float* row_lse, float* row_loss, float* loss, int flags,
                        void* stream);
-/* dlogits bf16 [*, ld_dlogits] rows listed in `rows` get (softmax - onehot) * (*gscale) / n_rows;
- * the caller zero-fills the buffer beforehand.  gscale: device fp32 scalar (upstream d loss).
- * ld_dlogits < 0 selects the COMPACT layout: row r of dlogits (pitch -ld_dlogits) receives rows[r]. */
+/* dlogits bf16 rows get (softmax - onehot) * (*gscale) / n_rows; in the dense layout the caller
+ * zero-fills the buffer beforehand.  gscale: device fp32 scalar (upstream d loss). */
 int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
                        const int64_t* tokens, const float* row_lse, const float* gscale,
-                       uint16_t* dlogits, int64_t ld_dlogits, void* stream);
+                       uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small memory-bound helpers around the GEMMs.
@@ -158,6 +161,8 @@ int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, in
 /* rows: dst[i,:] = src[rows[i],:] (gather) or dst[rows[i],:] = src[i,:] (scatter), bf16 width n. */
 int neko_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* rows, int n_rows, int n,
                           uint16_t* dst, int64_t ld_dst, void* stream);
+int neko_scatter_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* rows, int n_rows, int n,
+                           uint16_t* dst, int64_t ld_dst, void* stream);
 int neko_scatter_rows_add_f32(const uint16_t* src_bf16, int64_t ld_src, const int32_t* rows, int n_rows,
                               int n, float* dst, int64_t ld_dst, void* stream);
 
@@ -178,12 +183,12 @@ int neko_patch_resblock_bwd(const void* images, int is_u8, int n_img, int Himg, 
                             const float* gn_stats, const uint16_t* d_patches_bf16,
                             float* d_conv1_w, float* d_conv1_b, float* d_gn_w, float* d_gn_b,
                             float* d_conv2_w, float* d_conv2_b, void* stream);
-/* x[p,:] += row_tab[row_idx[p % (n_h*n_w) / n_w]] + col_tab[col_idx[p % n_w]] (embeddings.py:56-57,
- * 102-110) on fp32 [P,d]; the bins are computed by the host with the reference's own torch calls. */
-int neko_patch_pos_add(float* x, int P, int d, int n_h, int n_w, const int32_t* row_idx,
-                       const int32_t* col_idx, const float* row_tab, const float* col_tab, void* stream);
-int neko_patch_pos_bwd(const float* dx, int P, int d, int n_h, int n_w, const int32_t* row_idx,
-                       const int32_t* col_idx, float* d_row_tab, float* d_col_tab, void* stream);
+/* x[p,:] += row_tab[row_bin[p]] + col_tab[col_bin[p]] (embeddings.py:56-57,102-110) on fp32 [P,d]; the
+ * bins are computed by the host with the reference's own torch calls (keeps the train-mode RNG stream). */
+int neko_patch_pos_add(float* x, int P, int d, const int32_t* row_bin, const int32_t* col_bin,
+                       const float* row_tab, const float* col_tab, void* stream);
+int neko_patch_pos_bwd(const float* dx, int P, int d, const int32_t* row_bin, const int32_t* col_bin,
+                       float* d_row_tab, float* d_col_tab, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser step (train.py:127-133, trainer.py:181-186): global-norm clip + AdamW over one flat

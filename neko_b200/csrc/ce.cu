@@ -21,11 +21,11 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
 
 __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ logits, long long ld, int V,
                                                             const int32_t* __restrict__ rows, const int64_t* __restrict__ tokens,
-                                                            float* __restrict__ row_lse, float* __restrict__ row_loss) {
+                                                            float* __restrict__ row_lse, float* __restrict__ row_loss, int flags) {
   __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
   const int r = blockIdx.x;
   const long long pos = rows[r];
-  const float* z = logits + pos * ld;
+  const float* z = logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : pos) * ld;
   float m = -INFINITY, s = 0.f;
   const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   int start = 0;
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
                                                             const int32_t* __restrict__ rows, int n_rows,
                                                             const int64_t* __restrict__ tokens, const float* __restrict__ row_lse,
                                                             const float* __restrict__ gscale, bf16* __restrict__ dlogits, long long ldd,
-                                                            int compact) {
+                                                            int flags) {
   const int r = blockIdx.x;
   const long long pos = rows[r];
-  const float* z = logits + pos * ld;
-  bf16* dz = dlogits + (compact ? (long long)r : pos) * ldd;
+  const float* z = logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : pos) * ld;
+  bf16* dz = dlogits + ((flags & NEKO_CE_DLOGITS_COMPACT) ? (long long)r : pos) * ldd;
   const float lse = row_lse[r];
   const float g = __ldg(gscale) / (float)n_rows;
   const int tgt = (int)tokens[pos + 1];
@@ -119,11 +119,11 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
 extern "C" {
 
 int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
-                       float* row_lse, float* row_loss, float* loss, void* stream) {
+                       float* row_lse, float* row_loss, float* loss, int flags, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(logits && rows && tokens && row_lse && row_loss && loss, "masked_ce_fwd: null pointer");
   NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V, "masked_ce_fwd: bad sizes (V=%d n_rows=%d)", V, n_rows);
-  ce_fwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, tokens, row_lse, row_loss);
+  ce_fwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, tokens, row_lse, row_loss, flags);
   NEKO_LAUNCH_CHECK("ce_fwd_kernel");
   ce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_rows, loss);
   NEKO_LAUNCH_CHECK("ce_mean_kernel");
@@ -131,15 +131,13 @@ int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int3
 }
 
 int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
-                       const float* row_lse, const float* gscale, uint16_t* dlogits, int64_t ld_dlogits, void* stream) {
+                       const float* row_lse, const float* gscale, uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(logits && rows && tokens && row_lse && gscale && dlogits, "masked_ce_bwd: null pointer");
-  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V && (ld_dlogits >= V || -ld_dlogits >= V), "masked_ce_bwd: bad sizes");
-  // a negative ld_dlogits selects the compact layout: row r of dlogits <- rows[r]
-  const int compact = ld_dlogits < 0 ? 1 : 0;
-  const long long ldd = compact ? -ld_dlogits : ld_dlogits;
+  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V && ld_dlogits >= V, "masked_ce_bwd: bad sizes");
+  const long long ldd = ld_dlogits;
   ce_bwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, n_rows, tokens, row_lse, gscale,
-                                                             reinterpret_cast<bf16*>(dlogits), ldd, compact);
+                                                             reinterpret_cast<bf16*>(dlogits), ldd, flags);
   NEKO_LAUNCH_CHECK("ce_bwd_kernel");
   return NEKO_OK;
 }

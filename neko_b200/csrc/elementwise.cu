@@ -61,6 +61,22 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const bf16* __res
   }
 }
 
+__global__ void __launch_bounds__(256) scatter_rows_bf16_kernel(const bf16* __restrict__ src, long long ld_src, const int32_t* __restrict__ rows,
+                                                                int n_rows, int n, bf16* __restrict__ dst, long long ld_dst) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const bf16* s = src + (size_t)w * ld_src;
+  bf16* d = dst + (size_t)rows[w] * ld_dst;
+  if ((n & 7) == 0 && (ld_src & 7) == 0 && (ld_dst & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (int i = lane; i < (n >> 3); i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < n; i += 32) d[i] = s[i];
+  }
+}
+
 __global__ void __launch_bounds__(256) scatter_rows_add_kernel(const bf16* __restrict__ src, long long ld_src, const int32_t* __restrict__ rows,
                                                                int n_rows, int n, float* __restrict__ dst, long long ld_dst) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -118,6 +134,19 @@ int neko_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* ro
   gather_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows, n,
                                                                             reinterpret_cast<bf16*>(dst), ld_dst);
   NEKO_LAUNCH_CHECK("gather_rows_bf16_kernel");
+  return NEKO_OK;
+}
+
+int neko_scatter_rows_bf16(const uint16_t* src, int64_t ld_src, const int32_t* rows, int n_rows, int n, uint16_t* dst,
+                           int64_t ld_dst, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(src && rows && dst && n > 0 && n_rows >= 0, "scatter_rows: bad arguments");
+  if (n_rows == 0) return NEKO_OK;
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "scatter_rows: misaligned");
+  const long long blocks = ((long long)n_rows * 32 + 255) / 256;
+  scatter_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows, n,
+                                                                             reinterpret_cast<bf16*>(dst), ld_dst);
+  NEKO_LAUNCH_CHECK("scatter_rows_bf16_kernel");
   return NEKO_OK;
 }
 

@@ -113,22 +113,25 @@ def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[in
 # ------------------------------------------------------------------------------------------
 # masked cross entropy
 # ------------------------------------------------------------------------------------------
-def masked_ce_fwd(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torch.Tensor):
+CE_LOGITS_COMPACT, CE_DLOGITS_COMPACT = 1, 2
+
+
+def masked_ce_fwd(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torch.Tensor, flags: int = 0):
     """logits fp32 [N, ld]; rows int32 [n]; tokens int64 flat [N]."""
     n = rows.numel()
     row_lse = torch.empty(n, device=logits.device, dtype=torch.float32)
     row_loss = torch.empty(n, device=logits.device, dtype=torch.float32)
     loss = torch.empty((), device=logits.device, dtype=torch.float32)
     check(load().neko_masked_ce_fwd(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens),
-                                    _p(row_lse), _p(row_loss), _p(loss), stream_ptr()), "neko_masked_ce_fwd")
+                                    _p(row_lse), _p(row_loss), _p(loss), C.c_int(flags), stream_ptr()), "neko_masked_ce_fwd")
     return loss, row_lse, row_loss
 
 
-def masked_ce_bwd(logits, V, rows, tokens, row_lse, gscale, dlogits, compact: bool = False):
+def masked_ce_bwd(logits, V, rows, tokens, row_lse, gscale, dlogits, flags: int = 0):
     n = rows.numel()
     ld = dlogits.stride(-2)
     check(load().neko_masked_ce_bwd(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens),
-                                    _p(row_lse), _p(gscale), _p(dlogits), C.c_int64(-ld if compact else ld), stream_ptr()),
+                                    _p(row_lse), _p(gscale), _p(dlogits), C.c_int64(ld), C.c_int(flags), stream_ptr()),
           "neko_masked_ce_bwd")
 
 
@@ -155,6 +158,12 @@ def colsum(x_bf16: torch.Tensor, out: torch.Tensor, accumulate: bool = False, M:
 def gather_rows(src_bf16, rows, n: int, dst):
     check(load().neko_gather_rows_bf16(_p(src_bf16), C.c_int64(src_bf16.stride(0)), _p(rows), C.c_int(rows.numel()), C.c_int(n),
                                        _p(dst), C.c_int64(dst.stride(0)), stream_ptr()), "neko_gather_rows_bf16")
+    return dst
+
+
+def scatter_rows(src_bf16, rows, n: int, dst):
+    check(load().neko_scatter_rows_bf16(_p(src_bf16), C.c_int64(src_bf16.stride(0)), _p(rows), C.c_int(rows.numel()), C.c_int(n),
+                                        _p(dst), C.c_int64(dst.stride(0)), stream_ptr()), "neko_scatter_rows_bf16")
     return dst
 
 

@@ -1,0 +1,804 @@
+"""GatoPolicy -- drop-in for gato/policy/gato_policy.py:18 (GatoPolicy) on B200.
+
+Same constructor, attributes, ``state_dict`` key layout, ``forward`` / ``tokenize_input_dicts``
+signatures and return dtypes as the reference; everything underneath runs through the C ABI of
+``include/neko_b200.h`` (hand-written sm_100a kernels).  There is no CPU path: constructing the policy
+on a non-CUDA device, or without ``libneko_b200.so``, raises.
+
+Design:
+  * parameters live in ONE flat fp32 arena, gradients in a second one with the same layout (reverse
+    execution order, so data-parallel buckets complete front to back during backward); every
+    ``nn.Parameter`` / ``.grad`` is a view.  One kernel casts the arena to the bf16 operand copy.
+  * ``forward(inputs, compute_loss=True)`` is a single autograd node: the host plans the batch
+    (``packing.build_plan``), one H2D copy moves it, then ~14 kernel launches per layer run forward;
+    ``loss.backward()`` runs the hand-written backward and writes straight into the gradient arena.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from .._lib import TokParams, _p, check, load, stream_ptr
+from .embeddings import ImageEmbedding, _AffineParams, _EmbeddingParams, _LinearParams
+from .input_tokenizers import ContinuousTokenizer
+from .packing import BatchPlan, Stager, build_plan
+
+
+def _pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (trajectory_gpt2.py:120-359, 535-550)
+# --------------------------------------------------------------------------------------------------
+class _Conv1D(nn.Module):
+    """HF Conv1D: weight [in, out], y = x @ W + b; N(0, 0.02) / zeros (trajectory_gpt2.py:375-386)."""
+
+    def __init__(self, nf: int, nx: int):
+        super().__init__()
+        self.nf = nf
+        self.weight = nn.Parameter(torch.empty(nx, nf))
+        self.bias = nn.Parameter(torch.zeros(nf))
+        nn.init.normal_(self.weight, std=0.02)
+
+
+class _Attention(nn.Module):
+    def __init__(self, nx: int, n_ctx: int):
+        super().__init__()
+        # buffers kept for state_dict compatibility (trajectory_gpt2.py:127-130); the kernels derive the
+        # causal structure arithmetically
+        self.register_buffer("bias", torch.tril(torch.ones((n_ctx, n_ctx), dtype=torch.uint8)).view(1, 1, n_ctx, n_ctx))
+        self.register_buffer("masked_bias", torch.tensor(-1e4))
+        self.c_attn = _Conv1D(3 * nx, nx)
+        self.c_proj = _Conv1D(nx, nx)
+
+
+class _MLP(nn.Module):
+    def __init__(self, n_state: int, nx: int, gate: bool):
+        super().__init__()
+        self.c_fc = _Conv1D(n_state, nx)
+        self.c_proj = _Conv1D(nx, n_state)
+        if gate:
+            self.gated_layer = _LinearParams(nx, n_state)
+            nn.init.normal_(self.gated_layer.weight, std=0.02)
+            nn.init.zeros_(self.gated_layer.bias)
+        else:
+            self.gated_layer = None
+
+
+class _Block(nn.Module):
+    def __init__(self, nx: int, n_ctx: int, gate: bool):
+        super().__init__()
+        self.ln_1 = _AffineParams(nx)
+        self.attn = _Attention(nx, n_ctx)
+        self.ln_2 = _AffineParams(nx)
+        self.mlp = _MLP(4 * nx, nx, gate)
+
+
+class _GPT2Config:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class GPT2Model(nn.Module):
+    """Container for the decoder parameters (gato/transformers/trajectory_gpt2.py:535-550)."""
+
+    def __init__(self, config: _GPT2Config):
+        super().__init__()
+        self.config = config
+        self.wte = _EmbeddingParams(config.vocab_size, config.n_embd, std=0.02)  # never used (wpe/wte removed, :540,698-701)
+        self.drop = nn.Dropout(config.embd_pdrop)
+        self.h = nn.ModuleList([_Block(config.n_embd, config.n_ctx, config.gate) for _ in range(config.n_layer)])
+        self.ln_f = _AffineParams(config.n_embd)
+
+    def forward(self, inputs_embeds=None, attention_mask=None, **kw):
+        owner = getattr(self, "_owner", None)
+        if owner is None:
+            raise RuntimeError("GPT2Model must be owned by a GatoPolicy")
+        return {"last_hidden_state": owner()._decode_embeddings(inputs_embeds, attention_mask)}
+
+
+class _OfflineTextTokenizer:
+    """Stand-in when the GPT-2 BPE tables cannot be loaded (no hub access): the hot path only reads
+    ``vocab_size`` (gato_policy.py:57-60)."""
+
+    vocab_size = 50257
+
+    def encode(self, *_a, **_k):
+        raise RuntimeError("GPT-2 tokenizer files are not available offline")
+
+    decode = encode
+
+
+def _load_text_tokenizer(name: str):
+    try:
+        from transformers import AutoTokenizer
+        return AutoTokenizer.from_pretrained(name)
+    except Exception:  # noqa: BLE001 - offline / missing files
+        return _OfflineTextTokenizer()
+
+
+# --------------------------------------------------------------------------------------------------
+# one fused autograd node for forward(inputs, ...)
+# --------------------------------------------------------------------------------------------------
+class _FusedStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, policy, state, *params):
+        logits, loss = policy._engine_forward(state)
+        ctx.policy = policy
+        ctx.state = state
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(logits)
+        if loss is None:
+            loss = torch.zeros((), device=logits.device)
+            ctx.mark_non_differentiable(loss)
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, _g_logits, g_loss):
+        ctx.policy._engine_backward(ctx.state, g_loss)
+        # gradients were written straight into the flat arena behind every parameter's .grad
+        return (None, None) + (None,) * ctx.n_params
+
+
+class _State:
+    """Everything one forward hands to its backward."""
+    pass
+
+
+class GatoPolicy(nn.Module):
+    def __init__(
+        self,
+        device: Union[torch.device, str],
+        embed_dim: int,
+        layers: int,
+        heads: int,
+        dropout: float,
+        activation_fn="gelu",
+        mu: int = 100,
+        M: int = 256,
+        patch_size: int = 16,
+        resid_mid_channels: int = 132,
+        num_groups: int = 32,
+        position_vocab_size: int = 128,
+        continuous_tokens: int = 1024,
+        discrete_tokens: int = 1024,
+        context_len=1024,
+        use_pos_encoding: bool = True,
+        use_patch_pos_encoding: bool = True,
+        pretrained_lm: Optional[str] = None,
+        flash: bool = False,
+        tokenizer_model_name: str = "gpt2",
+        pad_seq: bool = False,
+        text_tokenizer=None,
+    ):
+        super().__init__()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.NekoError("neko_b200.GatoPolicy runs on CUDA (sm_100) only; there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        with torch.cuda.device(dev):
+            _lib.require_device()
+        if pretrained_lm is not None:
+            raise NotImplementedError("--pretrained_lm needs the HF hub (SURVEY.md section 8(f).4)")
+        assert embed_dim % heads == 0
+        if (embed_dim // heads) not in (16, 32, 64, 128):
+            raise NotImplementedError(f"head dim {embed_dim // heads} not supported (16/32/64/128)")
+        self.context_len = context_len
+        self.pad_seq = pad_seq
+        self.text_tokenizer = text_tokenizer if text_tokenizer is not None else _load_text_tokenizer(tokenizer_model_name)
+        self.text_tokens = self.text_tokenizer.vocab_size
+        self.continuous_tokens = continuous_tokens
+        self.discrete_tokens = discrete_tokens
+        self.vocab_size = self.text_tokens + self.discrete_tokens + self.continuous_tokens
+        self.token_starts = {"text": 0, "continuous": self.text_tokens, "discrete": self.text_tokens + self.continuous_tokens}
+        self.token_ends = {"text": self.text_tokens - 1, "continuous": self.text_tokens + self.continuous_tokens - 1,
+                           "discrete": self.text_tokens + self.continuous_tokens + self.discrete_tokens - 1}
+        gate = False
+        if activation_fn == "geglu":
+            gate = True
+            activation_fn = "gelu"
+        if activation_fn != "gelu":
+            raise NotImplementedError(f"activation_fn={activation_fn!r}: only 'gelu' (erf) and 'geglu' exist in the reference CLI")
+        self.heads = heads
+        self.layers = layers
+        self.dropout = dropout
+        self.mu, self.M = mu, M
+        self.patch_size = patch_size
+        config = _GPT2Config(vocab_size=1, n_embd=embed_dim, n_head=heads, n_layer=layers, resid_pdrop=dropout,
+                             attn_pdrop=dropout, embd_pdrop=0.1, n_positions=context_len, n_ctx=context_len,
+                             n_inner=embed_dim * 4, activation_function=activation_fn, flash=flash, gate=gate,
+                             layer_norm_epsilon=1e-5)
+        with torch.device(dev):
+            self.transformer = GPT2Model(config)
+            self.embed_token = _EmbeddingParams(self.vocab_size, embed_dim)
+            self.embed_dim = embed_dim
+            self.predict_token = _LinearParams(embed_dim, self.vocab_size, bias=False)
+            self.separator_token = nn.Parameter(torch.zeros(embed_dim))
+            self.continuous_action_tokenizer = ContinuousTokenizer(use_mu_law=False, mu=mu, M=M, n_bins=self.continuous_tokens,
+                                                                   offset=self.token_starts["continuous"])
+            self.continuous_obs_tokenizer = ContinuousTokenizer(use_mu_law=True, mu=mu, M=M, n_bins=self.continuous_tokens,
+                                                                offset=self.token_starts["continuous"])
+            self.use_patch_pos_encoding = use_patch_pos_encoding
+            self.image_embedding = ImageEmbedding(embed_dim=embed_dim, patch_size=patch_size, resid_mid_channels=resid_mid_channels,
+                                                  num_groups=num_groups, position_vocab_size=position_vocab_size,
+                                                  use_pos_encoding=use_patch_pos_encoding)
+            self.use_pos_encoding = use_pos_encoding
+            self.pos_embed_observation = _EmbeddingParams(context_len, embed_dim)
+        ref = weakref.ref(self)
+        object.__setattr__(self.transformer, "_owner", ref)
+        object.__setattr__(self.image_embedding, "_owner", ref)
+        # engine knobs
+        self.head_mode = "dense"        # 'dense' | 'rows' (identical results; 'rows' compacts the loss rows in backward)
+        self.materialize_logits = True  # False: head evaluated on loss rows only, forward returns logits=None
+        self._Vp = _pad_to(self.vocab_size, 64)
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._stager = Stager(dev)
+        self._generation = 0
+        self._bf16_versions = None
+        self._grad_live = False
+        self.grad_ready_hook = None     # callable(lo, hi): arena range [lo, hi) is final (data-parallel buckets)
+        self.launches = 0
+        self._build_arena()
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def module(self):
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    # flat parameter / gradient arenas
+    # ------------------------------------------------------------------------------------------
+    def _arena_order(self) -> List[str]:
+        names = ["predict_token.weight", "transformer.ln_f.weight", "transformer.ln_f.bias"]
+        for i in reversed(range(self.layers)):
+            p = f"transformer.h.{i}."
+            names += [p + "mlp.c_proj.weight", p + "mlp.c_proj.bias"]
+            if self.transformer.config.gate:
+                names += [p + "mlp.gated_layer.weight", p + "mlp.gated_layer.bias"]
+            names += [p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "ln_2.weight", p + "ln_2.bias",
+                      p + "attn.c_proj.weight", p + "attn.c_proj.bias", p + "attn.c_attn.weight", p + "attn.c_attn.bias",
+                      p + "ln_1.weight", p + "ln_1.bias"]
+        names += ["pos_embed_observation.weight", "separator_token", "embed_token.weight"]
+        names += [n for n, _ in self.named_parameters() if n.startswith("image_embedding.")]
+        names += ["transformer.wte.weight"]
+        return names
+
+    def _build_arena(self):
+        params = dict(self.named_parameters())
+        order = self._arena_order()
+        assert set(order) == set(params), set(params) ^ set(order)
+        offs, total = {}, 0
+        for n in order:
+            offs[n] = total
+            numel = params[n].numel()
+            if n == "predict_token.weight":  # zero rows up to the padded vocabulary: TMA reads them
+                numel = self._Vp * self.embed_dim
+            total += _pad_to(numel, 64)
+        arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+        for n in order:
+            p = params[n]
+            view = arena[offs[n]:offs[n] + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._param_arena = arena
+        self._grad_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._bf16_arena = torch.zeros(total, dtype=torch.bfloat16, device=self.device)
+        self._offs = offs
+        self._order = order
+        self._params = params
+        self._bf16_versions = None
+        self._grad_live = False
+
+    def _check_arena(self):
+        """Parameters must still be views of the arena (a ``.to()`` / ``.half()`` would replace them)."""
+        base = self._param_arena.data_ptr()
+        for n in ("predict_token.weight", "transformer.wte.weight"):
+            if self._params[n].data_ptr() != base + 4 * self._offs[n] or self._params[n].dtype != torch.float32:
+                self._build_arena()
+                break
+
+    def _gview(self, name: str) -> torch.Tensor:
+        p = self._params[name]
+        o = self._offs[name]
+        return self._grad_arena[o:o + p.numel()].view(p.shape)
+
+    def _bview(self, name: str, rows: Optional[int] = None) -> torch.Tensor:
+        p = self._params[name]
+        o = self._offs[name]
+        if rows is not None:
+            return self._bf16_arena[o:o + rows * p.shape[1]].view(rows, p.shape[1])
+        return self._bf16_arena[o:o + p.numel()].view(p.shape)
+
+    def _refresh_bf16(self):
+        vers = tuple(p._version for p in self._params.values())
+        if vers != self._bf16_versions:
+            ops.cast_bf16(self._param_arena, self._bf16_arena)
+            self.launches += 1
+            self._bf16_versions = vers
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+        self._grad_live = False
+
+    def _begin_grads(self, has_images: bool):
+        """Start (or continue) a gradient-accumulation cycle; returns True when accumulating.  Parameters that
+        take no part in the step keep ``grad is None`` exactly like the reference's autograd (transformer.wte
+        always; the image stack when the batch has no images)."""
+        live = self._grad_live
+        if live:
+            for n in ("predict_token.weight", "embed_token.weight"):
+                g = self._params[n].grad
+                if g is None or g.data_ptr() != self._grad_arena.data_ptr() + 4 * self._offs[n]:
+                    live = False
+        if not live:
+            self._grad_arena.zero_()
+            for n, p in self._params.items():
+                p.grad = None
+        for n, p in self._params.items():
+            if p.grad is not None or n == "transformer.wte.weight":
+                continue
+            if n.startswith("image_embedding."):
+                if not has_images or (".patch_pos_encoding." in n and not self.use_patch_pos_encoding):
+                    continue
+            if n == "pos_embed_observation.weight" and not self.use_pos_encoding:
+                continue
+            p.grad = self._gview(n)
+        self._grad_live = True
+        return live
+
+    # ------------------------------------------------------------------------------------------
+    # workspace
+    # ------------------------------------------------------------------------------------------
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        t = self._ws.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------------------------------
+    # public API
+    # ------------------------------------------------------------------------------------------
+    def forward(self, inputs: Optional[list] = None, compute_loss=False, **kwargs):
+        """gato_policy.py:156-192.  Returns (logits [B,S,V] fp32, loss or None)."""
+        self._check_arena()
+        if inputs is not None:
+            state = self._plan(inputs, compute_loss)
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values())
+            state.need_grad = need_grad
+            if need_grad:
+                logits, loss = _FusedStep.apply(self, state, *self._params.values())
+            else:
+                logits, loss = self._engine_forward(state)
+            if not compute_loss:
+                loss = None
+            return logits, loss
+        assert "token_embeddings" in kwargs and "tokens" in kwargs and "token_target_masks" in kwargs and "token_masks" in kwargs, \
+            "if inputs is None, must provide embeddings, tokens, and masks"
+        emb, tokens = kwargs["token_embeddings"], kwargs["tokens"]
+        tmask, mask = kwargs["token_target_masks"], kwargs["token_masks"]
+        if emb.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("gradients through caller-supplied token_embeddings are not implemented; pass `inputs`")
+        B, S, d = emb.shape
+        with torch.no_grad():
+            hf = self._decode_hidden(emb, mask)
+            full = self._head(hf, B * S)
+            logits = full.view(B, S, self._Vp)[:, :, :self.vocab_size]
+            loss = None
+            if compute_loss:
+                lm = (mask[:, :-1] * tmask[:, 1:]).reshape(-1) > 0
+                pos = torch.arange(B * S, device=self.device).view(B, S)[:, :-1].reshape(-1)[lm].to(torch.int32)
+                loss, _, _ = ops.masked_ce_fwd(full, self.vocab_size, pos, tokens.reshape(-1).contiguous())
+        return logits, loss
+
+    def tokenize_input_dicts(self, inputs: list):
+        """gato_policy.py:195-432 -> (token_embeddings fp32 [B,S,d], tokens int64 [B,S], token_target_masks fp32,
+        token_masks fp32).  Tensors are detached (training goes through ``forward(inputs=...)``)."""
+        self._check_arena()
+        with torch.no_grad():
+            state = self._plan(inputs, False)
+            state.need_grad = False
+            self._embed(state)
+        B, W, d = state.plan.B, state.plan.width, self.embed_dim
+        return (state.x0.view(B, W, d).clone(), state.tokens.view(B, W).clone(), state.tmask.view(B, W).clone(),
+                state.mask.view(B, W).clone())
+
+    # ------------------------------------------------------------------------------------------
+    # planning + upload
+    # ------------------------------------------------------------------------------------------
+    def _plan(self, inputs, compute_loss) -> _State:
+        st = _State()
+        plan = build_plan(inputs, patch_size=self.patch_size, context_len=self.context_len, pad_seq=self.pad_seq)
+        st.plan = plan
+        st.compute_loss = bool(compute_loss)
+        # train-mode patch bins consume the global CPU RNG per image-bearing sample, rows first (embeddings.py:92-95)
+        st.row_bins = st.col_bins = None
+        if plan.n_patch_rows and self.use_patch_pos_encoding and any(g.tensors for g in plan.image_groups):
+            ppe = self.image_embedding.patch_pos_encoding
+            rb = np.zeros(plan.n_patch_rows, dtype=np.int32)
+            cb = np.zeros(plan.n_patch_rows, dtype=np.int32)
+            per_sample = {}
+            for g in plan.image_groups:
+                for k, b in enumerate(g.sample_idx):
+                    per_sample[b] = (g, k)
+            for b in sorted(per_sample):  # batch order = the reference's draw order
+                g, k = per_sample[b]
+                n_h, n_w = g.height // self.patch_size, g.width // self.patch_size
+                hp, wp = ppe.positions(n_h, n_w)
+                T = int(g.tensors[k].shape[0])
+                off = g.patch_off[k]
+                rb[off:off + T * n_h * n_w] = np.tile(np.repeat(hp.numpy(), n_w), T)
+                cb[off:off + T * n_h * n_w] = np.tile(np.tile(wp.numpy(), n_h), T)
+            st.row_bins, st.col_bins = rb, cb
+        descs, fv, iv, first_valid, loss_rows, h2d = self._stager.upload(plan)
+        st.descs, st.fvals, st.ivals, st.first_valid, st.loss_rows = descs, fv, iv, first_valid, loss_rows
+        st.h2d_bytes = h2d
+        return st
+
+    def _tok_params(self, plan: BatchPlan) -> TokParams:
+        return TokParams(mu=float(self.mu), M=float(self.M), n_bins=int(self.continuous_tokens),
+                         cont_start=int(self.token_starts["continuous"]), disc_start=int(self.token_starts["discrete"]),
+                         vocab=int(self.vocab_size), use_pos=int(bool(self.use_pos_encoding)), seq_len=int(plan.seq_len),
+                         width=int(plan.width), ctx_rows=int(self.context_len))
+
+    # ------------------------------------------------------------------------------------------
+    # image front end
+    # ------------------------------------------------------------------------------------------
+    def _image_forward(self, st: _State):
+        plan = st.plan
+        d = self.embed_dim
+        if plan.n_patch_rows == 0:
+            st.patch_emb = None
+            return
+        pe = self._buf("patch_emb", (plan.n_patch_rows, d), torch.float32)
+        st.patch_emb = pe
+        st.img_groups = []
+        ie = self.image_embedding
+        rb = ie.patch_embedding
+        lib = load()
+        for gi, g in enumerate(plan.image_groups):
+            if not g.tensors:
+                continue
+            n_px = 3 * g.height * g.width
+            buf = self._buf(f"img{gi}", (g.n_frames * n_px,), torch.uint8 if g.is_u8 else torch.float32)
+            o = 0
+            for t in g.tensors:  # pinned / device sources copy asynchronously; no host-side concatenation
+                n = t.numel()
+                buf[o:o + n].view(t.shape).copy_(t, non_blocking=True)
+                if not t.is_cuda:
+                    st.h2d_bytes += n * t.element_size()
+                o += n
+            n_h, n_w = g.height // self.patch_size, g.width // self.patch_size
+            P = g.n_frames * n_h * n_w
+            row0 = g.patch_off[0]
+            patches = self._buf(f"patches{gi}", (P, 3 * self.patch_size ** 2), torch.bfloat16)
+            stats = self._buf(f"gnstats{gi}", (P, rb.num_groups, 2), torch.float32)
+            check(lib.neko_patch_resblock_fwd(_p(buf), C.c_int(int(g.is_u8)), C.c_int(g.n_frames), C.c_int(g.height), C.c_int(g.width),
+                                              C.c_int(self.patch_size), C.c_int(rb.mid_channels), C.c_int(rb.num_groups),
+                                              _p(rb.conv1.weight), _p(rb.conv1.bias), _p(rb.gn2.weight), _p(rb.gn2.bias),
+                                              _p(rb.conv2.weight), _p(rb.conv2.bias), _p(patches), _p(stats), stream_ptr()),
+                  "neko_patch_resblock_fwd")
+            out = pe[row0:row0 + P]
+            ops.gemm(patches, self._bview("image_embedding.post_embedding_projection.weight"), epilogue=ops.EPI_F32,
+                     out=out, bias=ie.post_embedding_projection.bias)
+            self.launches += 2
+            st.img_groups.append((gi, g, buf, patches, stats, row0, P))
+        if st.row_bins is not None:
+            bins = torch.from_numpy(np.concatenate([st.row_bins, st.col_bins]))
+            dev_bins = self._buf("patch_bins", (2 * plan.n_patch_rows,), torch.int32)
+            dev_bins.copy_(bins, non_blocking=True)
+            st.h2d_bytes += bins.numel() * 4
+            st.dev_row_bins, st.dev_col_bins = dev_bins[:plan.n_patch_rows], dev_bins[plan.n_patch_rows:]
+            for (_gi, _g, _buf, _patches, _stats, row0, P) in st.img_groups:
+                check(lib.neko_patch_pos_add(_p(pe[row0:row0 + P]), C.c_int(P), C.c_int(d), _p(st.dev_row_bins[row0:row0 + P]),
+                                             _p(st.dev_col_bins[row0:row0 + P]),
+                                             _p(ie.patch_pos_encoding.height_pos_embedding.weight),
+                                             _p(ie.patch_pos_encoding.width_pos_embedding.weight), stream_ptr()),
+                      "neko_patch_pos_add")
+                self.launches += 1
+        for off, emb in plan.precomputed_patch:  # caller-supplied image_embeddings (gato_policy.py:286-287)
+            n = emb.shape[0] * emb.shape[1]
+            pe[off:off + n].copy_(emb.reshape(n, d).to(torch.float32), non_blocking=True)
+
+    def _embed_images_standalone(self, images: torch.Tensor) -> torch.Tensor:
+        """ImageEmbedding.forward(x) for callers such as predict_response (gato_policy.py:489)."""
+        with torch.no_grad():
+            st = self._plan([{"images": images}], False)
+            st.need_grad = False
+            self._refresh_bf16()
+            self._image_forward(st)
+        T = images.shape[0]
+        return st.patch_emb.view(T, -1, self.embed_dim).clone()
+
+    # ------------------------------------------------------------------------------------------
+    # forward engine
+    # ------------------------------------------------------------------------------------------
+    def _embed(self, st: _State):
+        plan = st.plan
+        d = self.embed_dim
+        N = plan.B * plan.width
+        self._refresh_bf16()
+        self._image_forward(st)
+        keep = st.need_grad
+        st.tokens = self._buf("tokens", (N,), torch.int64)
+        st.tmask = self._buf("tmask", (N,), torch.float32)
+        st.mask = self._buf("mask", (N,), torch.float32)
+        st.x0 = self._buf("x.0" if keep else "x.a", (N, d), torch.float32)
+        prm = self._tok_params(plan)
+        st.tok_params = prm
+        check(load().neko_tokenize_embed_fwd(_p(st.descs), C.c_int(plan.B), C.c_int(d), C.byref(prm), _p(st.fvals), _p(st.ivals),
+                                             _p(st.patch_emb), _p(self.embed_token.weight), _p(self.pos_embed_observation.weight),
+                                             _p(self.separator_token), _p(st.tokens), _p(st.tmask), _p(st.mask), _p(st.x0), _p(None),
+                                             stream_ptr()), "neko_tokenize_embed_fwd")
+        self.launches += 1
+
+    def _check_dropout(self):
+        if self.training and (self.dropout > 0 or self.transformer.drop.p > 0):
+            raise NotImplementedError(
+                "dropout is not implemented in the CUDA path yet: construct with dropout=0 and set "
+                "model.transformer.drop.p = 0 (embd_pdrop is 0.1 in the reference whatever --dropout says, SURVEY quirk 8)")
+
+    def _decoder(self, st: _State, x: torch.Tensor, B: int, W: int, S_valid: int, first_valid: torch.Tensor, keep: bool):
+        """L pre-LN blocks + ln_f (trajectory_gpt2.py:322-358, 779).  x fp32 [N,d] -> hf bf16 [N,d]."""
+        self._check_dropout()
+        if self.transformer.config.gate:
+            raise NotImplementedError("activation_fn='geglu' (SURVEY.md section 8(f).4) is not implemented in the CUDA path")
+        d, H = self.embed_dim, self.heads
+        N = B * W
+        eps = self.transformer.config.layer_norm_epsilon
+        acts = []
+        for i, blk in enumerate(self.transformer.h):
+            tag = f".{i}" if keep else ""
+            pre = f"transformer.h.{i}."
+            ln1 = self._buf("ln1" + tag, (N, d), torch.bfloat16)
+            m1 = self._buf("m1" + tag, (N,), torch.float32)
+            r1 = self._buf("r1" + tag, (N,), torch.float32)
+            ops.layernorm_fwd(x, blk.ln_1.weight, blk.ln_1.bias, eps, ln1, m1, r1)
+            qkv = self._buf("qkv" + tag, (N, 3 * d), torch.bfloat16)
+            ops.gemm(ln1, self._bview(pre + "attn.c_attn.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=qkv, bias=blk.attn.c_attn.bias)
+            att = self._buf("att" + tag, (N, d), torch.bfloat16)
+            lse = self._buf("lse" + tag, (B, H, W), torch.float32)
+            ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse)
+            x1 = self._buf(f"x.{2 * i + 1}" if keep else "x.b", (N, d), torch.float32)
+            ops.gemm(att, self._bview(pre + "attn.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x1, aux=x,
+                     bias=blk.attn.c_proj.bias)
+            ln2 = self._buf("ln2" + tag, (N, d), torch.bfloat16)
+            m2 = self._buf("m2" + tag, (N,), torch.float32)
+            r2 = self._buf("r2" + tag, (N,), torch.float32)
+            ops.layernorm_fwd(x1, blk.ln_2.weight, blk.ln_2.bias, eps, ln2, m2, r2)
+            fpre = self._buf("fpre" + tag, (N, 4 * d), torch.bfloat16)
+            fact = self._buf("fact" + tag, (N, 4 * d), torch.bfloat16)
+            ops.gemm(ln2, self._bview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
+                     bias=blk.mlp.c_fc.bias)
+            x2 = self._buf(f"x.{2 * i + 2}" if keep else "x.a", (N, d), torch.float32)
+            ops.gemm(fact, self._bview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
+                     bias=blk.mlp.c_proj.bias)
+            self.launches += 7
+            if keep:
+                acts.append((x, ln1, m1, r1, qkv, att, lse, x1, ln2, m2, r2, fpre, fact))
+            x = x2
+        hf = self._buf("hf", (N, d), torch.bfloat16)
+        mf = self._buf("mf", (N,), torch.float32)
+        rf = self._buf("rf", (N,), torch.float32)
+        ops.layernorm_fwd(x, self.transformer.ln_f.weight, self.transformer.ln_f.bias, eps, hf, mf, rf)
+        self.launches += 1
+        if keep:
+            st.acts, st.x_last, st.hf, st.mf, st.rf = acts, x, hf, mf, rf
+        return hf
+
+    def _head(self, hf: torch.Tensor, n_rows: int) -> torch.Tensor:
+        """predict_token (gato_policy.py:172): fp32 logits [n_rows, Vp] (columns >= V are exact zeros).  Freshly
+        allocated (torch's caching allocator) because the caller keeps the tensor."""
+        logits = torch.empty(n_rows, self._Vp, dtype=torch.float32, device=self.device)
+        ops.gemm(hf, self._bview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_F32, out=logits, N=self._Vp)
+        self.launches += 1
+        return logits
+
+    def _decode_embeddings(self, emb: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+        B, S, d = emb.shape
+        return self._decode_hidden(emb, mask).view(B, S, d).to(torch.float32)
+
+    def _decode_hidden(self, emb: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Decoder on caller-supplied embeddings (the kwargs path used by predict_*, gato_policy.py:160-169);
+        returns ln_f output as the bf16 [B*S, d] head operand."""
+        with torch.no_grad():
+            self._refresh_bf16()
+            B, S, d = emb.shape
+            x = self._buf("x.a", (B * S, d), torch.float32)
+            x.copy_(emb.reshape(B * S, d).to(torch.float32))
+            if mask is None:
+                fv = torch.zeros(B, dtype=torch.int32, device=self.device)
+            else:  # first valid key per sample; right padding is never visible to a valid (causal) query
+                fv = (mask.to(self.device).cumsum(1) == 0).sum(1).to(torch.int32)
+            st = _State()
+            return self._decoder(st, x, B, S, S, fv, keep=False)
+
+    def _engine_forward(self, st: _State):
+        plan = st.plan
+        B, W, d, V = plan.B, plan.width, self.embed_dim, self.vocab_size
+        N = B * W
+        self._generation += 1
+        st.generation = self._generation
+        keep = st.need_grad
+        self._embed(st)
+        hf = self._decoder(st, st.x0, B, W, plan.seq_len, st.first_valid, keep)
+        n_rows = int(plan.loss_rows.shape[0])
+        st.n_rows = n_rows
+        loss = None
+        if self.materialize_logits:
+            full = self._head(hf, N)
+            logits = full.view(B, W, self._Vp)[:, :, :V]
+            st.logits_full = full
+            if st.compute_loss:
+                if n_rows == 0:
+                    loss = torch.full((), float("nan"), device=self.device)  # mean over an empty selection
+                else:
+                    loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens)
+                    self.launches += 2
+        else:
+            logits = torch.empty(0, device=self.device)
+            if st.compute_loss and n_rows:
+                hc = self._buf("hf_rows", (n_rows, d), torch.bfloat16)
+                ops.gather_rows(hf, st.loss_rows, d, hc)
+                full = self._head(hc, n_rows)
+                st.logits_full, st.hf_rows = full, hc
+                loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens, flags=ops.CE_LOGITS_COMPACT)
+                self.launches += 3
+        return logits, loss
+
+    # ------------------------------------------------------------------------------------------
+    # backward engine
+    # ------------------------------------------------------------------------------------------
+    def _notify(self, first: str, last: str):
+        if self.grad_ready_hook is not None:
+            lo = self._offs[first]
+            hi = self._offs[last] + _pad_to(self._params[last].numel(), 64)
+            if last == "predict_token.weight":
+                hi = self._offs[last] + _pad_to(self._Vp * self.embed_dim, 64)
+            self.grad_ready_hook(lo, hi)
+
+    def _engine_backward(self, st: _State, g_loss: torch.Tensor):
+        if st.generation != self._generation:
+            raise RuntimeError("backward() called after a newer forward reused the activation workspace")
+        if not st.compute_loss or st.n_rows == 0:
+            raise RuntimeError("nothing to differentiate: forward ran with compute_loss=False or selected no loss rows")
+        plan = st.plan
+        B, W, d, V, Vp, H = plan.B, plan.width, self.embed_dim, self.vocab_size, self._Vp, self.heads
+        N = B * W
+        n_rows = st.n_rows
+        acc = self._begin_grads(bool(plan.n_patch_rows and getattr(st, 'img_groups', None)))
+        gscale = g_loss.detach().to(torch.float32).reshape(())
+        G = self._gview
+        Wb = self._bview
+
+        # ---- head + cross entropy -----------------------------------------------------------------
+        compact_logits = not self.materialize_logits
+        if self.head_mode == "rows" or compact_logits:
+            dl = self._buf("dlogits_rows", (n_rows, Vp), torch.bfloat16)
+            if n_rows * Vp:
+                dl.zero_()  # pad columns V..Vp must be zero (K tail of the dgrad GEMM)
+            flags = ops.CE_DLOGITS_COMPACT | (ops.CE_LOGITS_COMPACT if compact_logits else 0)
+            ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl, flags=flags)
+            if compact_logits:
+                hc = st.hf_rows
+            else:
+                hc = self._buf("hf_rows", (n_rows, d), torch.bfloat16)
+                ops.gather_rows(st.hf, st.loss_rows, d, hc)
+            ops.gemm(dl, hc, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,
+                     M=V, N=d, K=n_rows)
+            dhc = self._buf("dhf_rows", (n_rows, d), torch.bfloat16)
+            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_BF16, out=dhc, M=n_rows, N=d, K=Vp)
+            dhf = self._buf("dhf", (N, d), torch.bfloat16)
+            dhf.zero_()
+            ops.scatter_rows(dhc, st.loss_rows, d, dhf)
+            self.launches += 7
+        else:
+            dl = self._buf("dlogits", (N, Vp), torch.bfloat16)
+            dl.zero_()
+            ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl)
+            ops.gemm(dl, st.hf, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,
+                     M=V, N=d, K=N)
+            dhf = self._buf("dhf", (N, d), torch.bfloat16)
+            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_BF16, out=dhf, M=N, N=d, K=Vp)
+            self.launches += 4
+        self._notify("predict_token.weight", "predict_token.weight")
+
+        # ---- ln_f -------------------------------------------------------------------------------------
+        dx = self._buf("dx", (N, d), torch.float32)
+        dx.zero_()
+        dxb = self._buf("dx_bf16", (N, d), torch.bfloat16)
+        lnf = self.transformer.ln_f
+        ops.layernorm_bwd(dhf, st.x_last, lnf.weight, st.mf, st.rf, dx, G("transformer.ln_f.weight"), G("transformer.ln_f.bias"), dxb)
+        self.launches += 2
+
+        # ---- blocks, last to first ------------------------------------------------------------------------
+        for i in reversed(range(self.layers)):
+            blk = self.transformer.h[i]
+            pre = f"transformer.h.{i}."
+            (x0, ln1, m1, r1, qkv, att, lse, x1, ln2, m2, r2, fpre, fact) = st.acts[i]
+            # MLP: x2 = x1 + gelu(ln2 @ Wfc + b) @ Wproj + b
+            ops.gemm(fact, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_proj.weight"), accumulate=acc,
+                     M=4 * d, N=d, K=N)
+            ops.colsum(dxb, G(pre + "mlp.c_proj.bias"), accumulate=True)
+            dpre = self._buf("dfpre", (N, 4 * d), torch.bfloat16)
+            ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre)
+            ops.gemm(ln2, dpre, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_fc.weight"), accumulate=acc,
+                     M=d, N=4 * d, K=N)
+            ops.colsum(dpre, G(pre + "mlp.c_fc.bias"), accumulate=True)
+            dln = self._buf("dln", (N, d), torch.bfloat16)
+            ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_BF16, out=dln)
+            ops.layernorm_bwd(dln, x1, blk.ln_2.weight, m2, r2, dx, G(pre + "ln_2.weight"), G(pre + "ln_2.bias"), dxb)
+            # attention: x1 = x0 + attn(ln1 @ Wqkv + b) @ Wproj + b
+            ops.gemm(att, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "attn.c_proj.weight"), accumulate=acc,
+                     M=d, N=d, K=N)
+            ops.colsum(dxb, G(pre + "attn.c_proj.bias"), accumulate=True)
+            datt = self._buf("datt", (N, d), torch.bfloat16)
+            ops.gemm(dxb, Wb(pre + "attn.c_proj.weight"), epilogue=ops.EPI_BF16, out=datt)
+            dqkv = self._buf("dqkv", (N, 3 * d), torch.bfloat16)
+            delta = self._buf("delta", (B, H, W), torch.float32)
+            ops.attention_bwd(qkv.view(B, W, 3 * d), att.view(B, W, d), datt.view(B, W, d), lse, st.first_valid, H, plan.seq_len,
+                              dqkv.view(B, W, 3 * d), delta)
+            ops.gemm(ln1, dqkv, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "attn.c_attn.weight"), accumulate=acc,
+                     M=d, N=3 * d, K=N)
+            ops.colsum(dqkv, G(pre + "attn.c_attn.bias"), accumulate=True)
+            ops.gemm(dqkv, Wb(pre + "attn.c_attn.weight"), epilogue=ops.EPI_BF16, out=dln)
+            ops.layernorm_bwd(dln, x0, blk.ln_1.weight, m1, r1, dx, G(pre + "ln_1.weight"), G(pre + "ln_1.bias"), dxb)
+            self.launches += 17
+            self._notify(pre + "mlp.c_proj.weight", pre + "ln_1.bias")
+
+        # ---- embeddings ---------------------------------------------------------------------------------------
+        dpe = None
+        if plan.n_patch_rows and getattr(st, "img_groups", None):
+            dpe = self._buf("d_patch_emb", (plan.n_patch_rows, d), torch.float32)
+            dpe.zero_()
+        check(load().neko_embed_bwd(_p(st.descs), C.c_int(B), C.c_int(d), C.byref(st.tok_params), _p(st.tokens), _p(dx),
+                                    _p(G("embed_token.weight")), _p(G("pos_embed_observation.weight")), _p(G("separator_token")),
+                                    _p(dpe), stream_ptr()), "neko_embed_bwd")
+        self.launches += 1
+        if dpe is not None:
+            self._image_backward(st, dpe, acc)
+        self._notify("pos_embed_observation.weight", self._order[-1])
+
+    def _image_backward(self, st: _State, dpe: torch.Tensor, acc: bool):
+        d = self.embed_dim
+        ie = self.image_embedding
+        rb = ie.patch_embedding
+        G = self._gview
+        lib = load()
+        pp = "image_embedding.patch_embedding."
+        for (gi, g, buf, patches, stats, row0, P) in st.img_groups:
+            gslice = dpe[row0:row0 + P]
+            if st.row_bins is not None:
+                check(lib.neko_patch_pos_bwd(_p(gslice), C.c_int(P), C.c_int(d), _p(st.dev_row_bins[row0:row0 + P]),
+                                             _p(st.dev_col_bins[row0:row0 + P]),
+                                             _p(G("image_embedding.patch_pos_encoding.height_pos_embedding.weight")),
+                                             _p(G("image_embedding.patch_pos_encoding.width_pos_embedding.weight")), stream_ptr()),
+                      "neko_patch_pos_bwd")
+            gb = self._buf(f"dpe_bf16_{gi}", (P, d), torch.bfloat16)
+            ops.cast_bf16(gslice, gb)
+            ops.colsum(gb, G("image_embedding.post_embedding_projection.bias"), accumulate=True)
+            ops.gemm(gb, patches, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("image_embedding.post_embedding_projection.weight"),
+                     accumulate=True, M=d, N=patches.shape[1], K=P)
+            dpatch = self._buf(f"dpatches{gi}", (P, patches.shape[1]), torch.bfloat16)
+            ops.gemm(gb, self._bview("image_embedding.post_embedding_projection.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=dpatch)
+            check(lib.neko_patch_resblock_bwd(_p(buf), C.c_int(int(g.is_u8)), C.c_int(g.n_frames), C.c_int(g.height), C.c_int(g.width),
+                                              C.c_int(self.patch_size), C.c_int(rb.mid_channels), C.c_int(rb.num_groups),
+                                              _p(rb.conv1.weight), _p(rb.conv1.bias), _p(rb.gn2.weight), _p(rb.gn2.bias),
+                                              _p(rb.conv2.weight), _p(stats), _p(dpatch), _p(G(pp + "conv1.weight")),
+                                              _p(G(pp + "conv1.bias")), _p(G(pp + "gn2.weight")), _p(G(pp + "gn2.bias")),
+                                              _p(G(pp + "conv2.weight")), _p(G(pp + "conv2.bias")), stream_ptr()),
+                  "neko_patch_resblock_bwd")
+            self.launches += 6

@@ -60,6 +60,7 @@ def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad
     n_f = n_i = 0
     groups: List[ImageGroup] = []
     pre_patch: List[Tuple[int, torch.Tensor]] = []
+    pre_samples = []
     n_patch_rows = 0
     lengths = []
     tgt_patterns = []
@@ -111,7 +112,7 @@ def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad
             if _is_present(s, "image_embeddings"):
                 emb = s["image_embeddings"]
                 n_img, n_p = int(emb.shape[0]), int(emb.shape[1])
-                pre_patch.append((n_patch_rows, emb))
+                pre_samples.append((b, emb, n_img * n_p))
             else:
                 im = s["images"]
                 assert im.dim() == 4 and im.shape[1] == 3, "images must be [T,3,H,W]"
@@ -127,12 +128,9 @@ def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad
                     groups.append(grp)
                 grp.tensors.append(im)
                 grp.sample_idx.append(b)
-                grp.patch_off.append(n_patch_rows)
                 grp.n_frames += n_img
             check_T(n_img)
             d.n_patches = n_p
-            d.patch_off = n_patch_rows
-            n_patch_rows += n_img * n_p
         if _is_present(s, "continuous_obs"):
             t = s["continuous_obs"]
             check_T(int(t.shape[0]))
@@ -163,6 +161,18 @@ def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad
         pat[d.n_patches:d.n_patches + d.n_text] = 1
         pat[n_obs + 1:] = 1
         tgt_patterns.append(np.tile(pat, T))
+
+    # patch rows: one contiguous range per image group (one kernel launch each), then caller-supplied embeddings
+    for g in groups:
+        n_p = (g.height // patch_size) * (g.width // patch_size)
+        for k, b in enumerate(g.sample_idx):
+            g.patch_off.append(n_patch_rows)
+            descs[b].patch_off = n_patch_rows
+            n_patch_rows += int(g.tensors[k].shape[0]) * n_p
+    for b, emb, n in pre_samples:
+        pre_patch.append((n_patch_rows, emb))
+        descs[b].patch_off = n_patch_rows
+        n_patch_rows += n
 
     S = max(lengths)
     width = context_len if (pad_seq and context_len > S) else S

@@ -223,7 +223,7 @@ def test_masked_ce(ops, V, ld):
     ops.masked_ce_bwd(store, V, rows, tokens.reshape(-1), row_lse, gs, dl)
     assert (dl[:, :V].float() - z.grad).abs().max().item() < 2 ** -8 * z.grad.abs().max().item() + 1e-6  # bf16 rounding
     dlc = torch.zeros(rows.numel(), ld, device="cuda", dtype=torch.bfloat16)
-    ops.masked_ce_bwd(store, V, rows, tokens.reshape(-1), row_lse, gs, dlc, compact=True)
+    ops.masked_ce_bwd(store, V, rows, tokens.reshape(-1), row_lse, gs, dlc, flags=ops.CE_DLOGITS_COMPACT)
     assert torch.equal(dlc, dl[rows.long()])
 
 

@@ -1,0 +1,263 @@
+"""Parity of the CUDA hot path (through the GatoPolicy drop-in and the C ABI) against the CPU oracle on the
+same seeded inputs, and against the golden fixtures generated from the reference.  GPU only (-m gpu).
+
+Gates (BASELINE.json north_star): ids / masks bit-exact; logits max-abs <= 2e-2 on valid rows; loss relative
+<= 1e-3; gradients reported as cosine / relative error per parameter."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gato_oracle as O
+from oracle.make_golden import SMALL_CASES, small_batch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+LOSS_RTOL = 1e-3
+
+
+class _Tok:
+    def __init__(self, n):
+        self.vocab_size = n
+
+
+def make_policy(cfg: O.GatoConfig, weights=None, train=False):
+    from neko_b200.policy import GatoPolicy
+    m = GatoPolicy(device="cuda", embed_dim=cfg.embed_dim, layers=cfg.layers, heads=cfg.heads, dropout=0.0,
+                   activation_fn=cfg.activation_fn, mu=cfg.mu, M=cfg.M, patch_size=cfg.patch_size,
+                   resid_mid_channels=cfg.resid_mid_channels, num_groups=cfg.num_groups,
+                   position_vocab_size=cfg.position_vocab_size, continuous_tokens=cfg.continuous_tokens,
+                   discrete_tokens=cfg.discrete_tokens, context_len=cfg.context_len,
+                   use_pos_encoding=cfg.use_pos_encoding, use_patch_pos_encoding=cfg.use_patch_pos_encoding,
+                   pad_seq=cfg.pad_seq, text_tokenizer=_Tok(cfg.text_tokens))
+    m.transformer.drop.p = 0.0
+    if weights is not None:
+        res = m.load_state_dict(weights, strict=False)
+        assert not res.unexpected_keys
+        assert all(k.endswith("attn.bias") or k.endswith("masked_bias") for k in res.missing_keys), res
+    m.train(train)
+    return m
+
+
+def test_continuous_tokenizer_bit_exact(golden_dir):
+    from neko_b200.policy.input_tokenizers import ContinuousTokenizer
+    g = np.load(os.path.join(golden_dir, "tokenizer_kat.npz"))
+    x = torch.from_numpy(g["x"]).cuda()
+    obs = ContinuousTokenizer(use_mu_law=True, mu=100, M=256, n_bins=1024, offset=50257).encode(x)
+    act = ContinuousTokenizer(use_mu_law=False, mu=100, M=256, n_bins=1024, offset=50257).encode(x)
+    assert obs.dtype == torch.int32
+    assert np.array_equal(obs.cpu().numpy(), g["obs_ids"])
+    assert np.array_equal(act.cpu().numpy(), g["act_ids"])
+    # a larger sweep against the oracle restatement (2M values incl. denormals and huge magnitudes)
+    rs = np.random.RandomState(123)
+    big = np.concatenate([rs.standard_normal(1_000_000) * 5, rs.uniform(-300, 300, 500_000),
+                          np.exp(rs.uniform(-40, 12, 500_000)) * rs.choice([-1, 1], 500_000)]).astype(np.float32)
+    cfg = O.GatoConfig()
+    got = ContinuousTokenizer(use_mu_law=True, mu=100, M=256, n_bins=1024, offset=50257).encode(torch.from_numpy(big).cuda())
+    assert np.array_equal(got.cpu().numpy(), O.discretize(big, True, cfg))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_tokenize_configs_bit_exact(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"tok_{name}.npz"))
+    cfg = O.GatoConfig(embed_dim=32, layers=1, heads=1, context_len=O.CONFIGS[name]["context_len"])
+    m = make_policy(cfg)
+    batch = O.synth_batch(name, seed=int(g["seed"]))
+    emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+    assert tok.dtype == torch.int64 and tm.dtype == torch.float32 and mk.dtype == torch.float32 and emb.dtype == torch.float32
+    assert np.array_equal(tok.cpu().numpy(), g["tokens"])
+    assert np.array_equal(tm.cpu().numpy(), g["target_masks"].astype(np.float32))
+    assert np.array_equal(mk.cpu().numpy(), g["token_masks"].astype(np.float32))
+    # padded embeddings are exact zeros
+    assert float(emb[mk == 0].abs().max()) == 0.0 if (mk == 0).any() else True
+
+
+def test_embeddings_match_oracle():
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w)
+    batch = small_batch("mixed", cfg.text_tokens)
+    emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+    tb = O.tokenize(batch, cfg)
+    ref = O.embed_and_interleave(batch, tb, w, cfg)
+    assert np.array_equal(tok.cpu().numpy(), tb.tokens)
+    err = (emb.cpu() - ref).abs()
+    is_patch = torch.zeros_like(mk.cpu(), dtype=torch.bool)
+    S = tb.tokens.shape[1]
+    for b, st in enumerate(tb.samples):
+        if st.n_patches:
+            n = st.ids.shape[0]
+            pat = np.zeros(st.tokens_per_timestep, bool)
+            pat[:st.n_patches] = True
+            is_patch[b, S - n:] = torch.from_numpy(np.tile(pat, st.n_timesteps))
+    # gathers / position adds are fp32 exact; patch rows go through bf16 tensor-core projection
+    assert float(err[~is_patch].max()) <= 1e-6
+    assert float(err[is_patch].max()) <= 3e-2
+
+
+def _grad_report(m, w):
+    rep = {}
+    for n, p in m.named_parameters():
+        ref = w[n].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        g = p.grad.detach().cpu().double().reshape(-1)
+        r = ref.double().reshape(-1)
+        denom = float(g.norm() * r.norm())
+        cos = float((g @ r) / denom) if denom > 0 else 1.0
+        rel = float((g - r).norm() / (r.norm() + 1e-12))
+        rep[n] = (cos, rel, float(r.norm()))
+    return rep
+
+
+@pytest.mark.parametrize("case", ["mixed", "dh128", "nopos"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_forward_backward_vs_oracle_and_golden(golden_dir, case, mode):
+    g = np.load(os.path.join(golden_dir, f"fwd_{case}_{mode}.npz"))
+    cfg = O.GatoConfig(**SMALL_CASES[case]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w, train=(mode == "train"))
+    batch = small_batch(case, cfg.text_tokens)
+    torch.manual_seed(77)
+    logits, loss = m(batch, compute_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    for t in w.values():
+        t.requires_grad_(True)
+    torch.manual_seed(77)
+    ref = O.forward(w, batch, cfg, compute_loss=True, training=(mode == "train"))
+    ref.loss.backward()
+
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == tuple(ref.logits.shape)
+    valid = ref.token_masks.bool()
+    lerr = (logits.detach().cpu() - ref.logits.detach())[valid].abs().max().item()
+    assert lerr <= LOGIT_TOL, f"logits max-abs {lerr}"
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    # the committed reference outputs
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    li = g["logit_idx"]
+    keep = g["token_masks"][li[:, 0], li[:, 1]] > 0
+    got = logits.detach().cpu().numpy()[li[:, 0], li[:, 1], li[:, 2]]
+    assert np.abs(got - g["logit_val"])[keep].max() <= LOGIT_TOL
+    rep = _grad_report(m, w)
+    bad = {n: v for n, v in rep.items() if v[2] > 1e-6 and (v[0] < 0.99 or v[1] > 0.12)}
+    assert not bad, f"gradient mismatch (cos, rel, ref-norm): {bad}"
+    # weight matrices of the decoder must be tight
+    tight = [v for n, v in rep.items() if n.endswith("c_fc.weight") or n.endswith("c_attn.weight") or n == "predict_token.weight"]
+    assert min(v[0] for v in tight) > 0.999
+
+
+def test_geglu_not_silently_wrong():
+    cfg = O.GatoConfig(**SMALL_CASES["geglu_padseq"]["cfg"])
+    m = make_policy(cfg, O.make_weights(cfg, seed=3))
+    with pytest.raises(NotImplementedError):
+        m(small_batch("geglu_padseq", cfg.text_tokens), compute_loss=True)
+
+
+def test_pad_seq_matches_oracle():
+    kw = dict(SMALL_CASES["geglu_padseq"]["cfg"])
+    kw["activation_fn"] = "gelu"
+    cfg = O.GatoConfig(**kw)
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w)
+    batch = small_batch("geglu_padseq", cfg.text_tokens)
+    logits, loss = m(batch, compute_loss=True)
+    ref = O.forward(w, batch, cfg, compute_loss=True)
+    assert logits.shape[1] == cfg.context_len
+    valid = ref.token_masks.bool()
+    assert (logits.detach().cpu() - ref.logits)[valid].abs().max().item() <= LOGIT_TOL
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+
+
+def test_head_modes_and_accumulation_agree():
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    batch = small_batch("mixed", cfg.text_tokens)
+    grads = {}
+    for mode in ("dense", "rows", "lean"):
+        m = make_policy(cfg, w)
+        m.head_mode = "rows" if mode != "dense" else "dense"
+        m.materialize_logits = mode != "lean"
+        _, loss = m(batch, compute_loss=True)
+        loss.backward()
+        grads[mode] = ({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, loss.item())
+    for mode in ("rows", "lean"):
+        assert abs(grads[mode][1] - grads["dense"][1]) < 1e-5
+        for n, gd in grads["dense"][0].items():
+            gr = grads[mode][0][n]
+            assert (gd - gr).norm().item() <= 2e-2 * gd.norm().item() + 1e-7, (mode, n)
+    # two backward passes accumulate (gradient accumulation, trainer.py:176)
+    m = make_policy(cfg, w)
+    for _ in range(2):
+        _, loss = m(batch, compute_loss=True)
+        loss.backward()
+    for n, gd in grads["dense"][0].items():
+        assert (m.get_parameter(n).grad - 2 * gd).norm().item() <= 2e-2 * (2 * gd).norm().item() + 1e-7, n
+    m.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+
+
+def test_state_dict_layout_and_errors():
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    m = make_policy(cfg)
+    keys = set(m.state_dict().keys())
+    expect = set(O.weight_shapes(cfg).keys())
+    for i in range(cfg.layers):
+        expect |= {f"transformer.h.{i}.attn.bias", f"transformer.h.{i}.attn.masked_bias"}
+    assert keys == expect
+    for k, shp in O.weight_shapes(cfg).items():
+        assert tuple(m.state_dict()[k].shape) == tuple(shp), k
+    with pytest.raises(AssertionError):
+        m([{"continuous_obs": torch.zeros(3, 2), "continuous_actions": torch.zeros(4, 1)}])
+    with pytest.raises(AssertionError):
+        m([{"images": torch.zeros(1, 3, 20, 32)}])
+    with pytest.raises(AssertionError):
+        m(None)
+    from neko_b200.policy import GatoPolicy
+    with pytest.raises(ValueError):  # the reference's own default 132 is not divisible by 32 groups
+        GatoPolicy(device="cuda", embed_dim=64, layers=1, heads=2, dropout=0.0, text_tokenizer=_Tok(64))
+    with pytest.raises(Exception):
+        GatoPolicy(device="cpu", embed_dim=64, layers=1, heads=2, dropout=0.0, resid_mid_channels=128)
+
+
+def test_kwargs_path_matches_inputs_path():
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w)
+    batch = small_batch("mixed", cfg.text_tokens)
+    with torch.no_grad():
+        logits, loss = m(batch, compute_loss=True)
+        emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+        logits2, loss2 = m(token_embeddings=emb, tokens=tok, token_target_masks=tm, token_masks=mk, compute_loss=True)
+    valid = mk.bool()
+    assert (logits - logits2)[valid].abs().max().item() < 1e-5
+    assert abs(loss.item() - loss2.item()) < 1e-5
+
+
+def test_cfg2_logits_loss_at_model_scale():
+    """d=768 L=6 H=24 (BASELINE configs[1]) at batch 6: tolerance gates at the real width / vocabulary."""
+    cfg = O.GatoConfig(**O.CONFIGS["cfg2"])
+    w = O.make_weights(cfg, seed=0, perturb=False)
+    m = make_policy(cfg, w)
+    batch = O.synth_batch("cfg2", seed=1234, batch=6)
+    logits, loss = m(batch, compute_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    for k in w:
+        w[k].requires_grad_(True)
+    ref = O.forward(w, batch, cfg, compute_loss=True)
+    ref.loss.backward()
+    tok = O.tokenize(batch, cfg)
+    assert np.array_equal(tok.tokens, ref.tokens.numpy())
+    lerr = (logits.detach().cpu() - ref.logits.detach()).abs().max().item()
+    print("cfg2 logits max-abs", lerr, "loss", loss.item(), ref.loss.item())
+    assert lerr <= LOGIT_TOL
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    rep = _grad_report(m, w)
+    worst = sorted(rep.items(), key=lambda kv: kv[1][0])[:5]
+    print("worst gradient cosines", worst)
+    assert all(v[0] > 0.98 for n, v in rep.items() if v[2] > 1e-7), worst
