@@ -91,10 +91,11 @@ int neko_embed_bwd(const neko_sample_desc* descs, int B, int d, const neko_tok_p
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * LayerNorm (ln_1 / ln_2 / ln_f, trajectory_gpt2.py:323,353,779). x fp32 [N,d] -> y bf16.
+ * LayerNorm (ln_1 / ln_2 / ln_f, trajectory_gpt2.py:323,353,779). x fp32 [N,d] -> y bf16 (fp16 if out_f16).
  * ------------------------------------------------------------------------------------------- */
-int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_bf16,
-                       float* mean, float* rstd, int N, int d, float eps, void* stream);
+int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_16,
+                       uint16_t* y2_bf16 /* nullable second copy */, float* mean, float* rstd, int N, int d,
+                       float eps, int out_f16, void* stream);
 /* dx_resid (fp32 [N,d]) += LN'(dy); optional bf16 copy of the updated dx_resid; dgamma/dbeta
  * fp32 [d] are accumulated (caller zeroes them). */
 int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean,
@@ -111,17 +112,38 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
  *             = 1: operand is MN-major (stored [K, M] / [K, N] row-major, leading dimension ld).
  * ------------------------------------------------------------------------------------------- */
 enum neko_epilogue {
-  NEKO_EPI_BF16 = 0,            /* C bf16 = acc (+bias)                                        */
+  NEKO_EPI_BF16 = 0,            /* C 16-bit = acc (+bias)                                       */
   NEKO_EPI_F32 = 1,             /* C fp32 = acc (+bias) (+= C when accumulate)                  */
-  NEKO_EPI_GELU_BF16 = 2,       /* C bf16 = acc+bias (pre-activation), C2 bf16 = gelu_erf(C)    */
+  NEKO_EPI_GELU_BF16 = 2,       /* C 16-bit = acc+bias (pre-activation), C2 16-bit = gelu_erf() */
   NEKO_EPI_RESID_F32 = 3,       /* C fp32 = acc + bias + aux_f32[m,n]   (residual add)          */
-  NEKO_EPI_DGELU_BF16 = 4,      /* C bf16 = acc * gelu_erf'(aux_bf16[m,n])                      */
-  NEKO_EPI_RESID_F32_BF16 = 5   /* as 3, plus C2 bf16 copy of the result                        */
+  NEKO_EPI_DGELU_BF16 = 4,      /* C 16-bit = acc * gelu_erf'(aux_bf16[m,n])                    */
+  NEKO_EPI_RESID_F32_BF16 = 5   /* as 3, plus C2 16-bit copy of the result                      */
 };
+/* 16-bit operands / outputs are bf16 unless the matching flag selects IEEE fp16 (same tensor-core rate,
+ * 3 more mantissa bits: the forward pass uses fp16 operands to meet the logits tolerance, gradients stay
+ * bf16 for range).  tcgen05 kind::f16 traps on mixed A/B formats, so NEKO_GEMM_A_F16 and NEKO_GEMM_B_F16 must
+ * be set together. */
+#define NEKO_GEMM_A_F16 1
+#define NEKO_GEMM_B_F16 2
+#define NEKO_GEMM_C_F16 4
+#define NEKO_GEMM_C2_F16 8
 
-int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t lda, int a_mn, const uint16_t* B,
-                   int64_t ldb, int b_mn, int epilogue, void* C, int64_t ldc, void* C2, int64_t ldc2,
-                   const float* bias, const void* aux, int64_t ld_aux, int accumulate, void* stream);
+typedef struct neko_gemm_desc {
+  int32_t M, N, K;
+  int32_t a_mn, b_mn;           /* operand majors, see above                                    */
+  int32_t epilogue;             /* enum neko_epilogue                                           */
+  int32_t accumulate;           /* NEKO_EPI_F32 only: C += result                               */
+  int32_t flags;                /* NEKO_GEMM_*_F16; A and B must share one 16-bit format         */
+  const void* A; int64_t lda;   /* leading dimensions in elements, multiples of 8               */
+  const void* B; int64_t ldb;
+  void* C;  int64_t ldc;
+  void* C2; int64_t ldc2;       /* second output of the GELU / RESID_F32_BF16 epilogues          */
+  void* C3; int64_t ldc3;       /* optional bf16 copy of C2 (GELU epilogue): the wgrad operand   */
+  const float* bias;            /* [N] or NULL                                                  */
+  const void* aux; int64_t ld_aux;
+} neko_gemm_desc;
+
+int neko_gemm(const neko_gemm_desc* host_desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Causal self-attention with left padding (Attention._attn, trajectory_gpt2.py:163-188, with the
@@ -130,12 +152,13 @@ int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t lda, int a_mn
  * Sample b attends keys in [first_valid[b], min(query, S_valid-1)]; rows outside [first_valid[b], S_valid)
  * (left padding, right padding of --pad_seq) are written as zeros.
  * ------------------------------------------------------------------------------------------- */
-int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out, float* lse,
-                       int B, int S, int S_valid, int H, int dh, void* stream);
+int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out,
+                       uint16_t* out2_bf16 /* nullable second copy */, float* lse, int B, int S, int S_valid,
+                       int H, int dh, int out_f16, void* stream);
 /* dqkv bf16 [B,S,3*H*dh]; delta fp32 [B,H,S] is caller-provided scratch. */
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse,
                        const int32_t* first_valid, uint16_t* dqkv, float* delta, int B, int S, int S_valid,
-                       int H, int dh, void* stream);
+                       int H, int dh, int out_f16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Masked cross entropy (gato_policy.py:174-186).  rows int32 [n_rows]: flat source positions
@@ -156,6 +179,9 @@ int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int3
  * Small memory-bound helpers around the GEMMs.
  * ------------------------------------------------------------------------------------------- */
 int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+int neko_cast_f32_to_f16(const float* src, uint16_t* dst, int64_t n, void* stream);
+/* one read, two 16-bit copies (fp16 forward operand + bf16 backward operand of the weights) */
+int neko_cast_f32_to_f16_bf16(const float* src, uint16_t* dst_f16, uint16_t* dst_bf16, int64_t n, void* stream);
 /* out[n] (+)= sum_m X[m,n]; X bf16 [M, ld]  (bias gradients of Conv1D / Linear). */
 int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, int accumulate, void* stream);
 /* rows: dst[i,:] = src[rows[i],:] (gather) or dst[rows[i],:] = src[i,:] (scatter), bf16 width n. */
@@ -170,13 +196,14 @@ int neko_scatter_rows_add_f32(const uint16_t* src_bf16, int64_t ld_src, const in
  * Image patch embedding: ImageEmbedding.forward / ResidualBlock_V2 (embeddings.py:28-61,111-131)
  * up to (not including) post_embedding_projection, which is a neko_gemm_bf16 call.
  * images: `n_img` frames [3,Himg,Wimg] of fp32 (is_u8=0) or uint8 (is_u8=1), 0..255.
- * patches_out bf16 [n_img*n_h*n_w, 3*p*p]  (c p1 p2 flattening, embeddings.py:50).
+ * patches_out fp16 [n_img*n_h*n_w, 3*p*p]  (c p1 p2 flattening, embeddings.py:50).
  * Saved for backward: gn_stats fp32 [P, groups, 2] (mean, rstd).
  * ------------------------------------------------------------------------------------------- */
 int neko_patch_resblock_fwd(const void* images, int is_u8, int n_img, int Himg, int Wimg, int patch,
                             int C, int groups, const float* conv1_w, const float* conv1_b,
                             const float* gn_w, const float* gn_b, const float* conv2_w,
-                            const float* conv2_b, uint16_t* patches_out, float* gn_stats, void* stream);
+                            const float* conv2_b, uint16_t* patches_out, uint16_t* patches_out_bf16 /* nullable */,
+                            float* gn_stats, void* stream);
 int neko_patch_resblock_bwd(const void* images, int is_u8, int n_img, int Himg, int Wimg, int patch,
                             int C, int groups, const float* conv1_w, const float* conv1_b,
                             const float* gn_w, const float* gn_b, const float* conv2_w,

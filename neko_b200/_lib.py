@@ -31,6 +31,15 @@ class TokParams(C.Structure):
         "n_bins", "cont_start", "disc_start", "vocab", "use_pos", "seq_len", "width", "ctx_rows")]
 
 
+class GemmDesc(C.Structure):
+    """neko_gemm_desc (include/neko_b200.h)."""
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32),
+                ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("flags", C.c_int32),
+                ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64),
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("C2", C.c_void_p), ("ldc2", C.c_int64),
+                ("C3", C.c_void_p), ("ldc3", C.c_int64), ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_aux", C.c_int64)]
+
+
 EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_DGELU_BF16, EPI_RESID_F32_BF16 = range(6)
 
 _lib = None

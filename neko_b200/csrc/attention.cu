@@ -73,8 +73,8 @@ __device__ __forceinline__ void load_tile_t(Tile<ATT_BLK> dst, const bf16* __res
 // ---------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ first_valid,
-                                                               bf16* __restrict__ out, float* __restrict__ lse, int S, int S_valid,
-                                                               int H, float scale_log2) {
+                                                               bf16* __restrict__ out, bf16* __restrict__ out2, float* __restrict__ lse, int S,
+                                                               int S_valid, int H, float scale_log2, int out_f16) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Tile<DH> sQ{reinterpret_cast<bf16*>(smem_raw)};
   Tile<DH> sK{sQ.p + ATT_BLK * Tile<DH>::PITCH};
@@ -174,16 +174,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   const float inv_a = (l_a > 0.f) ? 1.f / l_a : 0.f, inv_b = (l_b > 0.f) ? 1.f / l_b : 0.f;
   const float kLn2 = 0.6931471805599453f;
   bf16* ob = out + (long long)b * S * d + h * DH;
+  bf16* ob2 = out2 ? out2 + (long long)b * S * d + h * DH : nullptr;
   if (row_a < S) {
 #pragma unroll
-    for (int n = 0; n < DH / 8; ++n)
-      *reinterpret_cast<uint32_t*>(ob + (long long)row_a * d + n * 8 + 2 * q) = pack_bf16x2(o[n][0] * inv_a, o[n][1] * inv_a);
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(ob + (long long)row_a * d + n * 8 + 2 * q) = pack_16x2(o[n][0] * inv_a, o[n][1] * inv_a, out_f16 != 0);
+      if (ob2) *reinterpret_cast<uint32_t*>(ob2 + (long long)row_a * d + n * 8 + 2 * q) = pack_bf16x2(o[n][0] * inv_a, o[n][1] * inv_a);
+    }
     if (q == 0) lse[((long long)b * H + h) * S + row_a] = (l_a > 0.f) ? (m_a * scale_log2 + log2f(l_a)) * kLn2 : INFINITY;
   }
   if (row_b < S) {
 #pragma unroll
-    for (int n = 0; n < DH / 8; ++n)
-      *reinterpret_cast<uint32_t*>(ob + (long long)row_b * d + n * 8 + 2 * q) = pack_bf16x2(o[n][2] * inv_b, o[n][3] * inv_b);
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(ob + (long long)row_b * d + n * 8 + 2 * q) = pack_16x2(o[n][2] * inv_b, o[n][3] * inv_b, out_f16 != 0);
+      if (ob2) *reinterpret_cast<uint32_t*>(ob2 + (long long)row_b * d + n * 8 + 2 * q) = pack_bf16x2(o[n][2] * inv_b, o[n][3] * inv_b);
+    }
     if (q == 0) lse[((long long)b * H + h) * S + row_b] = (l_b > 0.f) ? (m_b * scale_log2 + log2f(l_b)) * kLn2 : INFINITY;
   }
 }
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // ---------------------------------------------------------------------------------------------
 // delta[b,h,i] = sum_c dO[i,c] * O[i,c]
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                                         int B, int S, int H, int dh) {
+                                                         int B, int S, int H, int dh, int out_f16) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * S * H;
@@ -204,7 +209,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   const bf16* g = dout + bs * (long long)H * dh + (long long)h * dh;
   float acc = 0.f;
   for (int c = lane * 2; c < dh; c += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + c));
+    const uint32_t ou = *reinterpret_cast<const uint32_t*>(o + c);
+    const float2 a = out_f16 ? unpack_f16x2(ou) : unpack_bf16x2(ou);
     const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + c));
     acc += a.x * bb.x + a.y * bb.y;
   }
@@ -449,13 +455,13 @@ template <int DH>
 static size_t dq_smem() { return (size_t)(4 * ATT_BLK * Tile<DH>::PITCH + DH * Tile<ATT_BLK>::PITCH) * sizeof(bf16); }
 
 template <int DH>
-static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, float* lse, int B, int S, int S_valid, int H, cudaStream_t st) {
+static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int out_f16, cudaStream_t st) {
   const size_t smem = fwd_smem<DH>();
   cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_fwd)");
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(qkv, fv, out, lse, S, S_valid, H, scale_log2);
+  attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(qkv, fv, out, out2, lse, S, S_valid, H, scale_log2, out_f16);
   NEKO_LAUNCH_CHECK("attn_fwd_kernel");
   return NEKO_OK;
 }
@@ -482,26 +488,27 @@ static int launch_bwd(const bf16* qkv, const bf16* dout, const float* lse, const
 
 extern "C" {
 
-int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out, float* lse, int B, int S, int S_valid,
-                       int H, int dh, void* stream) {
+int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out, uint16_t* out2_bf16, float* lse, int B, int S,
+                       int S_valid, int H, int dh, int out_f16, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(qkv && first_valid && out && lse, "attention_fwd: null pointer");
   NEKO_REQUIRE(B > 0 && S > 0 && H > 0 && S_valid > 0 && S_valid <= S, "attention_fwd: bad sizes");
   NEKO_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention_fwd: misaligned");
   const bf16* x = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
+  bf16* o2 = reinterpret_cast<bf16*>(out2_bf16);
   cudaStream_t st = as_stream(stream);
   switch (dh) {
-    case 16: return launch_fwd<16>(x, first_valid, o, lse, B, S, S_valid, H, st);
-    case 32: return launch_fwd<32>(x, first_valid, o, lse, B, S, S_valid, H, st);
-    case 64: return launch_fwd<64>(x, first_valid, o, lse, B, S, S_valid, H, st);
-    case 128: return launch_fwd<128>(x, first_valid, o, lse, B, S, S_valid, H, st);
+    case 16: return launch_fwd<16>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
+    case 32: return launch_fwd<32>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
+    case 64: return launch_fwd<64>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
+    case 128: return launch_fwd<128>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
     default: set_error("attention: head dim %d not supported (16, 32, 64, 128)", dh); return NEKO_EINVAL;
   }
 }
 
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse, const int32_t* first_valid,
-                       uint16_t* dqkv, float* delta, int B, int S, int S_valid, int H, int dh, void* stream) {
+                       uint16_t* dqkv, float* delta, int B, int S, int S_valid, int H, int dh, int out_f16, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(qkv && out && dout && lse && first_valid && dqkv && delta, "attention_bwd: null pointer");
   NEKO_REQUIRE(B > 0 && S > 0 && H > 0 && S_valid > 0 && S_valid <= S, "attention_bwd: bad sizes");
@@ -511,7 +518,7 @@ int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t*
   const bf16* g = reinterpret_cast<const bf16*>(dout);
   bf16* dx = reinterpret_cast<bf16*>(dqkv);
   const long long warps = (long long)B * S * H;
-  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(o, g, delta, B, S, H, dh);
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(o, g, delta, B, S, H, dh, out_f16);
   NEKO_LAUNCH_CHECK("attn_delta_kernel");
   switch (dh) {
     case 16: return launch_bwd<16>(x, g, lse, delta, first_valid, dx, B, S, S_valid, H, st);

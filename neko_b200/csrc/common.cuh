@@ -1,6 +1,7 @@
 // Shared helpers for the neko_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -55,6 +56,23 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// fp16 conversions saturate at the largest finite half instead of overflowing to inf
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit pair in the requested format (f16 = IEEE half, else bfloat16)
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ uint16_t cvt_16(float v, bool f16) {
+  if (f16) { __half h = __float2half_rn(sat_f16(v)); return *reinterpret_cast<uint16_t*>(&h); }
+  bf16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);

@@ -3,20 +3,37 @@
 
 namespace neko {
 
-__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+__global__ void __launch_bounds__(256) cast_f32_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, int f16) {
   const long long nv = n >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(src);
   uint2* d2 = reinterpret_cast<uint2*>(dst);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
     const float4 v = __ldg(s4 + i);
-    d2[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    d2[i] = make_uint2(pack_16x2(v.x, v.y, f16 != 0), pack_16x2(v.z, v.w, f16 != 0));
   }
   for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16_rn(src[i]);
+    dst[i] = cvt_16(src[i], f16 != 0);
 }
 
 // out[n] += sum over a row chunk of X[m, n].  Block = 32 x 8 threads, each thread owns 2 adjacent columns.
+__global__ void __launch_bounds__(256) cast_f32_dual_kernel(const float* __restrict__ src, uint16_t* __restrict__ d16, uint16_t* __restrict__ dbf, long long n) {
+  const long long nv = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  uint2* a2 = reinterpret_cast<uint2*>(d16);
+  uint2* b2 = reinterpret_cast<uint2*>(dbf);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 v = __ldg(s4 + i);
+    a2[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+    b2[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    d16[i] = cvt_16(src[i], true);
+    dbf[i] = cvt_16(src[i], false);
+  }
+}
+
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, long long ld, int M, int N, int rows_per_cta,
                                                           float* __restrict__ out) {
   __shared__ float red[8][64];
@@ -91,7 +108,7 @@ __global__ void __launch_bounds__(256) scatter_rows_add_kernel(const bf16* __res
 
 extern "C" {
 
-int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
+static int cast_impl(const float* src, uint16_t* dst, int64_t n, int f16, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(src && dst && n >= 0, "cast: bad arguments");
   if (n == 0) return NEKO_OK;
@@ -100,8 +117,26 @@ int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stre
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
-  NEKO_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  cast_f32_16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, dst, n, f16);
+  NEKO_LAUNCH_CHECK("cast_f32_16_kernel");
+  return NEKO_OK;
+}
+
+int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) { return cast_impl(src, dst, n, 0, stream); }
+int neko_cast_f32_to_f16(const float* src, uint16_t* dst, int64_t n, void* stream) { return cast_impl(src, dst, n, 1, stream); }
+
+int neko_cast_f32_to_f16_bf16(const float* src, uint16_t* dst_f16, uint16_t* dst_bf16, int64_t n, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(src && dst_f16 && dst_bf16 && n >= 0, "cast: bad arguments");
+  if (n == 0) return NEKO_OK;
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_f16) & 7) == 0 &&
+               (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0, "cast: misaligned buffers");
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_dual_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, dst_f16, dst_bf16, n);
+  NEKO_LAUNCH_CHECK("cast_f32_dual_kernel");
   return NEKO_OK;
 }
 

@@ -42,10 +42,13 @@ struct GemmParams {
   long long ldc;
   void* C2;
   long long ldc2;
+  void* C3;
+  long long ldc3;
   const float* bias;
   const void* aux;
   long long ld_aux;
   int vec_ok;      // all epilogue pointers / leading dimensions allow 16-byte accesses
+  int flags;       // NEKO_GEMM_*_F16
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -138,11 +141,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
     }
   }
   const bool fast = (ncols == 32) && p.vec_ok;
+  const bool c_f16 = (p.flags & NEKO_GEMM_C_F16) != 0, c2_f16 = (p.flags & NEKO_GEMM_C2_F16) != 0;
   switch (p.epi) {
     case NEKO_EPI_BF16:
     case NEKO_EPI_GELU_BF16:
     case NEKO_EPI_DGELU_BF16: {
-      bf16* c = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col0;
+      uint16_t* c = reinterpret_cast<uint16_t*>(p.C) + row * p.ldc + col0;
       if (p.epi == NEKO_EPI_DGELU_BF16) {
         const bf16* a = reinterpret_cast<const bf16*>(p.aux) + row * p.ld_aux + col0;
         if (fast) {
@@ -168,27 +172,41 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
         uint4* c4 = reinterpret_cast<uint4*>(c);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                             pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+          c4[i] = make_uint4(pack_16x2(f[8 * i], f[8 * i + 1], c_f16), pack_16x2(f[8 * i + 2], f[8 * i + 3], c_f16),
+                             pack_16x2(f[8 * i + 4], f[8 * i + 5], c_f16), pack_16x2(f[8 * i + 6], f[8 * i + 7], c_f16));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < ncols) c[i] = __float2bfloat16_rn(f[i]);
+          if (i < ncols) c[i] = cvt_16(f[i], c_f16);
       }
       if (p.epi == NEKO_EPI_GELU_BF16) {
-        bf16* c2 = reinterpret_cast<bf16*>(p.C2) + row * p.ldc2 + col0;
+        uint16_t* c2 = reinterpret_cast<uint16_t*>(p.C2) + row * p.ldc2 + col0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
         if (fast) {
           uint4* c4 = reinterpret_cast<uint4*>(c2);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                               pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+            c4[i] = make_uint4(pack_16x2(f[8 * i], f[8 * i + 1], c2_f16), pack_16x2(f[8 * i + 2], f[8 * i + 3], c2_f16),
+                               pack_16x2(f[8 * i + 4], f[8 * i + 5], c2_f16), pack_16x2(f[8 * i + 6], f[8 * i + 7], c2_f16));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < ncols) c2[i] = __float2bfloat16_rn(f[i]);
+            if (i < ncols) c2[i] = cvt_16(f[i], c2_f16);
+        }
+        if (p.C3) {
+          uint16_t* c3 = reinterpret_cast<uint16_t*>(p.C3) + row * p.ldc3 + col0;
+          if (fast) {
+            uint4* c4 = reinterpret_cast<uint4*>(c3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                 pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) c3[i] = cvt_16(f[i], false);
+          }
         }
       }
       break;
@@ -224,17 +242,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
           if (i < ncols) c[i] = f[i];
       }
       if (p.epi == NEKO_EPI_RESID_F32_BF16) {
-        bf16* c2 = reinterpret_cast<bf16*>(p.C2) + row * p.ldc2 + col0;
+        uint16_t* c2 = reinterpret_cast<uint16_t*>(p.C2) + row * p.ldc2 + col0;
         if (fast) {
           uint4* c4 = reinterpret_cast<uint4*>(c2);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            c4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                               pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+            c4[i] = make_uint4(pack_16x2(f[8 * i], f[8 * i + 1], c2_f16), pack_16x2(f[8 * i + 2], f[8 * i + 3], c2_f16),
+                               pack_16x2(f[8 * i + 4], f[8 * i + 5], c2_f16), pack_16x2(f[8 * i + 6], f[8 * i + 7], c2_f16));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < ncols) c2[i] = __float2bfloat16_rn(f[i]);
+            if (i < ncols) c2[i] = cvt_16(f[i], c2_f16);
         }
       }
       break;
@@ -329,8 +347,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // instruction descriptor: fp32 accumulate, bf16 x bf16, M=128, N=BN, operand majors
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+      // instruction descriptor: fp32 accumulate, {f16|bf16} x {f16|bf16}, M=128, N=BN, operand majors
+      const uint32_t a_fmt = (p.flags & NEKO_GEMM_A_F16) ? 0u : 1u, b_fmt = (p.flags & NEKO_GEMM_B_F16) ? 0u : 1u;  // F16 = 0, BF16 = 1
+      const uint32_t idesc = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -418,25 +437,26 @@ struct MapKey {
   const void* ptr;
   unsigned long long inner, outer, ld;
   unsigned box_inner, box_outer;
+  int f16;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && f16 == o.f16;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.outer; h = h * 1000003u ^ k.ld;
-    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer;
+    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer; h = h * 1000003u ^ (size_t)k.f16;
     return h;
   }
 };
 
 // 2-D bf16 tensor [outer, inner] (inner contiguous, row pitch ld elements), box {box_inner, box_outer}.
 static int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner, unsigned long long outer, unsigned long long ld,
-                    unsigned box_inner, unsigned box_outer) {
+                    unsigned box_inner, unsigned box_outer, int f16) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, f16};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -448,7 +468,7 @@ static int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner,
   const cuuint64_t strides[1] = {ld * 2ull};
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -465,26 +485,33 @@ static int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner,
 
 }  // namespace neko
 
-extern "C" int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t lda, int a_mn, const uint16_t* B, int64_t ldb,
-                              int b_mn, int epilogue, void* C, int64_t ldc, void* C2, int64_t ldc2, const float* bias,
-                              const void* aux, int64_t ld_aux, int accumulate, void* stream) {
+extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   using namespace neko;
+  NEKO_REQUIRE(gd != nullptr, "gemm: null descriptor");
+  const int M = gd->M, N = gd->N, K = gd->K, a_mn = gd->a_mn, b_mn = gd->b_mn, epilogue = gd->epilogue;
+  const int accumulate = gd->accumulate, flags = gd->flags;
+  const void *A = gd->A, *B = gd->B, *aux = gd->aux;
+  void *C = gd->C, *C2 = gd->C2, *C3 = gd->C3;
+  const long long lda = gd->lda, ldb = gd->ldb, ldc = gd->ldc, ldc2 = gd->ldc2, ldc3 = gd->ldc3, ld_aux = gd->ld_aux;
+  const float* bias = gd->bias;
   NEKO_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
   NEKO_REQUIRE(A && B && C, "gemm: null operand");
   NEKO_REQUIRE(epilogue >= NEKO_EPI_BF16 && epilogue <= NEKO_EPI_RESID_F32_BF16, "gemm: unknown epilogue %d", epilogue);
+  NEKO_REQUIRE(((flags & NEKO_GEMM_A_F16) != 0) == ((flags & NEKO_GEMM_B_F16) != 0), "gemm: A and B must have the same 16-bit format (tcgen05 kind::f16 traps on mixed f16/bf16)");
   NEKO_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "gemm: operands must be 16-byte aligned");
-  NEKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements (TMA 16-byte pitch), got %lld %lld", (long long)lda, (long long)ldb);
+  NEKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements (TMA 16-byte pitch), got %lld %lld", lda, ldb);
   NEKO_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm: leading dimension smaller than the row length");
   if (epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_RESID_F32_BF16) NEKO_REQUIRE(C2 != nullptr, "gemm: epilogue %d needs C2", epilogue);
   if (epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_RESID_F32_BF16 || epilogue == NEKO_EPI_DGELU_BF16)
     NEKO_REQUIRE(aux != nullptr, "gemm: epilogue %d needs aux", epilogue);
   NEKO_REQUIRE(!accumulate || epilogue == NEKO_EPI_F32, "gemm: accumulate is only defined for NEKO_EPI_F32");
+  NEKO_REQUIRE(C3 == nullptr || epilogue == NEKO_EPI_GELU_BF16, "gemm: C3 is only defined for NEKO_EPI_GELU_BF16");
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
-  p.epi = epilogue; p.accumulate = accumulate;
-  p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.epi = epilogue; p.accumulate = accumulate; p.flags = flags;
+  p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.C3 = C3; p.ldc3 = ldc3; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
   // wide tiles when there are enough of them to fill the machine
   const int sms = sm_count();
   // tile width: fewest (waves x tile time); the narrow tile pays ~15% more operand traffic per flop
@@ -501,17 +528,18 @@ extern "C" int neko_gemm_bf16(int M, int N, int K, const uint16_t* A, int64_t ld
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   bool vec = al16(C) && (ldc % (out_bf16 ? 8 : 4) == 0);
   if (C2) vec = vec && al16(C2) && (ldc2 % 8 == 0);
+  if (C3) vec = vec && al16(C3) && (ldc3 % 8 == 0);
   if (bias) vec = vec && al16(bias);
   if (aux) vec = vec && al16(aux) && (ld_aux % (epilogue == NEKO_EPI_DGELU_BF16 ? 8 : 4) == 0);
   p.vec_ok = vec ? 1 : 0;
 
   CUtensorMap ma, mb;
   int rc;
-  if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM);
-  else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK);
+  if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM, flags & NEKO_GEMM_A_F16);
+  else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK, flags & NEKO_GEMM_A_F16);
   if (rc != NEKO_OK) return rc;
-  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN);
-  else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK);
+  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN, flags & NEKO_GEMM_B_F16);
+  else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK, flags & NEKO_GEMM_B_F16);
   if (rc != NEKO_OK) return rc;
 
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;

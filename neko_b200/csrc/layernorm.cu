@@ -12,9 +12,9 @@ constexpr int LN_MAX_D = 2048;  // NV (float4 per lane) is a template parameter:
 
 template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, bf16* __restrict__ y,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            int N, int d, float eps) {
+                                                            const float* __restrict__ beta, uint16_t* __restrict__ y,
+                                                            uint16_t* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int N, int d, float eps, int out_f16) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -47,16 +47,17 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
-  uint2* y2 = reinterpret_cast<uint2*>(y + (size_t)row * d);
+  uint2* yv = reinterpret_cast<uint2*>(y + (size_t)row * d);
+  uint2* yv2 = y2 ? reinterpret_cast<uint2*>(y2 + (size_t)row * d) : nullptr;
 #pragma unroll
   for (int k = 0; k < LN_MAX_VEC; ++k) {
     const int i = lane + k * 32;
     if (i < nv) {
       const float4 g = __ldg(g4 + i), bb = __ldg(b4 + i);
-      uint2 o;
-      o.x = pack_bf16x2((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
-      o.y = pack_bf16x2((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
-      y2[i] = o;
+      const float o0 = (v[k].x - mean) * rstd * g.x + bb.x, o1 = (v[k].y - mean) * rstd * g.y + bb.y;
+      const float o2 = (v[k].z - mean) * rstd * g.z + bb.z, o3 = (v[k].w - mean) * rstd * g.w + bb.w;
+      yv[i] = make_uint2(pack_16x2(o0, o1, out_f16 != 0), pack_16x2(o2, o3, out_f16 != 0));
+      if (yv2) yv2[i] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
     }
   }
 }
@@ -154,14 +155,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 
 extern "C" {
 
-int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_bf16, float* mean,
-                       float* rstd, int N, int d, float eps, void* stream) {
+int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, uint16_t* y_bf16, uint16_t* y2_bf16, float* mean,
+                       float* rstd, int N, int d, float eps, int out_f16, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(x && gamma && beta && y_bf16 && mean && rstd, "layernorm_fwd: null pointer");
   NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_fwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
   const int threads = 256;
   const long long blocks = ((long long)N * 32 + threads - 1) / threads;
-#define NEKO_LN_FWD(NV) layernorm_fwd_kernel<NV><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), mean, rstd, N, d, eps)
+#define NEKO_LN_FWD(NV) layernorm_fwd_kernel<NV><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, gamma, beta, y_bf16, y2_bf16, mean, rstd, N, d, eps, out_f16)
   const int need = (d / 4 + 31) / 32;
   if (need <= 1) NEKO_LN_FWD(1); else if (need <= 2) NEKO_LN_FWD(2); else if (need <= 4) NEKO_LN_FWD(4);
   else if (need <= 6) NEKO_LN_FWD(6); else if (need <= 8) NEKO_LN_FWD(8); else NEKO_LN_FWD(16);

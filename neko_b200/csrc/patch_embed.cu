@@ -1,7 +1,7 @@
 // Image patch embedding: ImageEmbedding.forward / ResidualBlock_V2 (embeddings.py:28-61,111-131).
 //
 //   x = (img/255*2 - 1)/sqrt(p)  ->  patchify 16x16  ->  h = conv1(GELU(x)) 3->C, 3x3, per-patch zero pad
-//   -> GroupNorm(groups) -> GELU -> conv2 C->3 -> x + .   -> flatten (c p1 p2) -> bf16 row of the projection GEMM
+//   -> GroupNorm(groups) -> GELU -> conv2 C->3 -> x + .   -> flatten (c p1 p2) -> fp16 row of the projection GEMM
 //
 // One CTA processes one patch at a time (persistent loop over patches, weights resident in shared memory),
 // the C x 256 intermediate never leaves shared memory (the unfused torch path writes / re-reads 131 KB per
@@ -24,7 +24,8 @@ struct PatchArgs {
   const void* images;
   int is_u8, n_img, Himg, Wimg, n_h, n_w, groups;
   const float *w1, *b1, *gw, *gb, *w2, *b2;
-  bf16* out;            // fwd: [P,768]
+  uint16_t* out;        // fwd: [P,768] fp16
+  uint16_t* out_bf;     // fwd: optional bf16 copy (wgrad operand)
   float* stats;         // [P, groups, 2]
   // backward only
   const bf16* dout;     // [P,768]
@@ -232,13 +233,14 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(Patch
     // residual + bias, write the (c p1 p2) row
     {
       const int y = tid >> 4, x = tid & 15, pi = plane_index(y, x);
-      bf16* o = a.out + (size_t)patch * (3 * PE_PX);
+      uint16_t* o = a.out + (size_t)patch * (3 * PE_PX);
 #pragma unroll
       for (int co = 0; co < 3; ++co) {
         float v = s.xin[co * PE_PX + tid] + a.b2[co];
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) v += s.red[(sl * 3 + co) * PE_PX + pi];
-        o[co * PE_PX + tid] = __float2bfloat16_rn(v);
+        o[co * PE_PX + tid] = cvt_16(v, true);
+        if (a.out_bf) a.out_bf[(size_t)patch * (3 * PE_PX) + co * PE_PX + tid] = cvt_16(v, false);
       }
     }
     __syncthreads();
@@ -462,7 +464,7 @@ extern "C" {
 
 int neko_patch_resblock_fwd(const void* images, int is_u8, int n_img, int Himg, int Wimg, int patch, int C, int groups,
                             const float* conv1_w, const float* conv1_b, const float* gn_w, const float* gn_b, const float* conv2_w,
-                            const float* conv2_b, uint16_t* patches_out, float* gn_stats, void* stream) {
+                            const float* conv2_b, uint16_t* patches_out, uint16_t* patches_out_bf16, float* gn_stats, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(images && conv1_w && conv1_b && gn_w && gn_b && conv2_w && conv2_b && patches_out && gn_stats, "patch_resblock_fwd: null pointer");
   int rc = check_patch_args(n_img, Himg, Wimg, patch, C, groups);
@@ -470,7 +472,7 @@ int neko_patch_resblock_fwd(const void* images, int is_u8, int n_img, int Himg, 
   PatchArgs a{};
   a.images = images; a.is_u8 = is_u8; a.n_img = n_img; a.Himg = Himg; a.Wimg = Wimg; a.n_h = Himg / patch; a.n_w = Wimg / patch;
   a.groups = groups; a.w1 = conv1_w; a.b1 = conv1_b; a.gw = gn_w; a.gb = gn_b; a.w2 = conv2_w; a.b2 = conv2_b;
-  a.out = reinterpret_cast<bf16*>(patches_out); a.stats = gn_stats;
+  a.out = patches_out; a.out_bf = patches_out_bf16; a.stats = gn_stats;
   const size_t smem = patch_smem_bytes(false);
   cudaError_t e = cudaFuncSetAttribute(patch_resblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(patch_fwd)");

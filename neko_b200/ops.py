@@ -12,7 +12,11 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_RESID_F32_BF16,  # noqa: F401
-                   SampleDesc, TokParams, _p, check, load, stream_ptr)
+                   GemmDesc, SampleDesc, TokParams, _p, check, load, stream_ptr)
+
+
+_16BIT = (torch.bfloat16, torch.float16)
+GEMM_A_F16, GEMM_B_F16, GEMM_C_F16, GEMM_C2_F16 = 1, 2, 4, 8
 
 
 def _cuda(*ts):
@@ -24,16 +28,21 @@ def _cuda(*ts):
 # ------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
-         out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-         aux: Optional[torch.Tensor] = None, accumulate: bool = False, M: Optional[int] = None,
-         N: Optional[int] = None, K: Optional[int] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, out3: Optional[torch.Tensor] = None,
+         bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, accumulate: bool = False,
+         M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
+         out_dtype: torch.dtype = torch.bfloat16):
     """C[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
-    a: bf16 [M,K] (a_mn=False) or [K,M] (a_mn=True); b: bf16 [N,K] or [K,N]; rows may be strided
+    a: 16-bit [M,K] (a_mn=False) or [K,M] (a_mn=True); b: same format, [N,K] or [K,N]; rows may be strided
     (stride(0) is the leading dimension)."""
-    _cuda(a, b, out, out2, bias, aux)
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    _cuda(a, b, out, out2, out3, bias, aux)
+    assert a.dtype in _16BIT and b.dtype == a.dtype, "A and B must share one 16-bit format"
     assert a.stride(1) == 1 and b.stride(1) == 1
     if M is None:
         M = a.shape[1] if a_mn else a.shape[0]
@@ -43,15 +52,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         N = b.shape[1] if b_mn else b.shape[0]
     bf16_out = epilogue in (EPI_BF16, EPI_GELU_BF16, EPI_DGELU_BF16)
     if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if bf16_out else torch.float32)
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype if bf16_out else torch.float32)
     if epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16) and out2 is None:
-        out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+        out2 = torch.empty(M, N, device=a.device, dtype=out_dtype)
     assert out.stride(1) == 1
-    check(load().neko_gemm_bf16(
-        C.c_int(M), C.c_int(N), C.c_int(K), _p(a), C.c_int64(a.stride(0)), C.c_int(int(a_mn)),
-        _p(b), C.c_int64(b.stride(0)), C.c_int(int(b_mn)), C.c_int(epilogue), _p(out), C.c_int64(out.stride(0)),
-        _p(out2), C.c_int64(out2.stride(0) if out2 is not None else 0), _p(bias), _p(aux),
-        C.c_int64(aux.stride(0) if aux is not None else 0), C.c_int(int(accumulate)), stream_ptr()), "neko_gemm_bf16")
+    flags = (GEMM_A_F16 | GEMM_B_F16) if a.dtype == torch.float16 else 0
+    flags |= GEMM_C_F16 if out.dtype == torch.float16 else 0
+    flags |= GEMM_C2_F16 if (out2 is not None and out2.dtype == torch.float16) else 0
+    gd = GemmDesc(M=M, N=N, K=K, a_mn=int(a_mn), b_mn=int(b_mn), epilogue=epilogue, accumulate=int(accumulate), flags=flags,
+                  A=a.data_ptr(), lda=a.stride(0), B=b.data_ptr(), ldb=b.stride(0), C=out.data_ptr(), ldc=out.stride(0),
+                  C2=_ptr(out2), ldc2=out2.stride(0) if out2 is not None else 0,
+                  C3=_ptr(out3), ldc3=out3.stride(0) if out3 is not None else 0,
+                  bias=_ptr(bias), aux=_ptr(aux), ld_aux=aux.stride(0) if aux is not None else 0)
+    check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
     if out2 is not None and epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16):
         return out, out2
     return out
@@ -60,17 +73,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 # ------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------
-def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, y=None, mean=None, rstd=None):
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, y=None, mean=None, rstd=None,
+                  out_dtype: torch.dtype = torch.bfloat16, y2=None):
     _cuda(x, gamma, beta)
     N, d = x.shape
     if y is None:
-        y = torch.empty(N, d, device=x.device, dtype=torch.bfloat16)
+        y = torch.empty(N, d, device=x.device, dtype=out_dtype)
     if mean is None:
         mean = torch.empty(N, device=x.device, dtype=torch.float32)
     if rstd is None:
         rstd = torch.empty(N, device=x.device, dtype=torch.float32)
-    check(load().neko_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), C.c_int(N), C.c_int(d),
-                                    C.c_float(eps), stream_ptr()), "neko_layernorm_fwd")
+    check(load().neko_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(y2), _p(mean), _p(rstd), C.c_int(N), C.c_int(d),
+                                    C.c_float(eps), C.c_int(int(y.dtype == torch.float16)), stream_ptr()), "neko_layernorm_fwd")
     return y, mean, rstd
 
 
@@ -83,17 +97,18 @@ def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf1
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
-def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid: Optional[int] = None, out=None, lse=None):
+def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid: Optional[int] = None, out=None, lse=None,
+                  out_dtype: torch.dtype = torch.bfloat16, out2=None):
     B, S, three_d = qkv.shape
     d = three_d // 3
     dh = d // H
     if out is None:
-        out = torch.empty(B, S, d, device=qkv.device, dtype=torch.bfloat16)
+        out = torch.empty(B, S, d, device=qkv.device, dtype=out_dtype)
     if lse is None:
         lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
-    check(load().neko_attention_fwd(_p(qkv), _p(first_valid), _p(out), _p(lse), C.c_int(B), C.c_int(S),
-                                    C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh), stream_ptr()),
-          "neko_attention_fwd")
+    check(load().neko_attention_fwd(_p(qkv), _p(first_valid), _p(out), _p(out2), _p(lse), C.c_int(B), C.c_int(S),
+                                    C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh),
+                                    C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_attention_fwd")
     return out, lse
 
 
@@ -106,7 +121,7 @@ def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[in
         delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
     check(load().neko_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(first_valid), _p(dqkv), _p(delta), C.c_int(B),
                                     C.c_int(S), C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh),
-                                    stream_ptr()), "neko_attention_bwd")
+                                    C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_attention_bwd")
     return dqkv
 
 
@@ -143,8 +158,16 @@ def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Te
     assert src.dtype == torch.float32 and src.is_contiguous()
     if dst is None:
         dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
-    check(load().neko_cast_f32_to_bf16(_p(src), _p(dst), C.c_int64(src.numel()), stream_ptr()), "neko_cast_f32_to_bf16")
+    fn = load().neko_cast_f32_to_f16 if dst.dtype == torch.float16 else load().neko_cast_f32_to_bf16
+    check(fn(_p(src), _p(dst), C.c_int64(src.numel()), stream_ptr()), "neko_cast_f32_to_16")
     return dst
+
+
+def cast_dual(src: torch.Tensor, dst_f16: torch.Tensor, dst_bf16: torch.Tensor):
+    """fp32 -> (fp16, bf16) in one pass."""
+    assert src.dtype == torch.float32 and dst_f16.dtype == torch.float16 and dst_bf16.dtype == torch.bfloat16
+    check(load().neko_cast_f32_to_f16_bf16(_p(src), _p(dst_f16), _p(dst_bf16), C.c_int64(src.numel()), stream_ptr()),
+          "neko_cast_f32_to_f16_bf16")
 
 
 def colsum(x_bf16: torch.Tensor, out: torch.Tensor, accumulate: bool = False, M: Optional[int] = None, N: Optional[int] = None):

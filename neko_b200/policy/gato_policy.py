@@ -240,6 +240,10 @@ class GatoPolicy(nn.Module):
         # engine knobs
         self.head_mode = "dense"        # 'dense' | 'rows' (identical results; 'rows' compacts the loss rows in backward)
         self.materialize_logits = True  # False: head evaluated on loss rows only, forward returns logits=None
+        # 16-bit format of the FORWARD operands (activations fed to GEMMs, weight copy).  fp16 has 3 more mantissa
+        # bits than bf16 at the same tensor-core rate and brings logits max-abs error from 2.1e-2 to ~6e-3 at
+        # d=768/L=6 (DESIGN.md "precision"); gradients stay bf16 for range, the residual stream stays fp32.
+        self.fwd_dtype = torch.float16
         self._Vp = _pad_to(self.vocab_size, 64)
         self._ws: Dict[str, torch.Tensor] = {}
         self._stager = Stager(dev)
@@ -268,9 +272,8 @@ class GatoPolicy(nn.Module):
             names += [p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "ln_2.weight", p + "ln_2.bias",
                       p + "attn.c_proj.weight", p + "attn.c_proj.bias", p + "attn.c_attn.weight", p + "attn.c_attn.bias",
                       p + "ln_1.weight", p + "ln_1.bias"]
-        names += ["pos_embed_observation.weight", "separator_token", "embed_token.weight"]
         names += [n for n, _ in self.named_parameters() if n.startswith("image_embedding.")]
-        names += ["transformer.wte.weight"]
+        names += ["pos_embed_observation.weight", "separator_token", "embed_token.weight", "transformer.wte.weight"]
         return names
 
     def _build_arena(self):
@@ -292,7 +295,12 @@ class GatoPolicy(nn.Module):
             p.data = view
         self._param_arena = arena
         self._grad_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self._bf16_arena = torch.zeros(total, dtype=torch.bfloat16, device=self.device)
+        # 16-bit operand copies of the GEMM weights: forward format + bf16 for dgrad (tcgen05 cannot mix formats);
+        # the embedding tables at the tail of the arena are only ever gathered in fp32 and are not copied
+        self._cast_end = offs["pos_embed_observation.weight"]
+        self._w16_arena = torch.zeros(self._cast_end, dtype=self.fwd_dtype, device=self.device)
+        self._wbf_arena = (self._w16_arena if self.fwd_dtype == torch.bfloat16
+                           else torch.zeros(self._cast_end, dtype=torch.bfloat16, device=self.device))
         self._offs = offs
         self._order = order
         self._params = params
@@ -312,17 +320,28 @@ class GatoPolicy(nn.Module):
         o = self._offs[name]
         return self._grad_arena[o:o + p.numel()].view(p.shape)
 
-    def _bview(self, name: str, rows: Optional[int] = None) -> torch.Tensor:
+    def _wview(self, name: str, rows: Optional[int] = None, bwd: bool = False) -> torch.Tensor:
+        """16-bit operand copy of a weight: forward format, or bf16 for the backward GEMMs."""
+        arena = self._wbf_arena if bwd else self._w16_arena
         p = self._params[name]
         o = self._offs[name]
         if rows is not None:
-            return self._bf16_arena[o:o + rows * p.shape[1]].view(rows, p.shape[1])
-        return self._bf16_arena[o:o + p.numel()].view(p.shape)
+            return arena[o:o + rows * p.shape[1]].view(rows, p.shape[1])
+        return arena[o:o + p.numel()].view(p.shape)
 
     def _refresh_bf16(self):
         vers = tuple(p._version for p in self._params.values())
+        if self._w16_arena.dtype != self.fwd_dtype:
+            self._w16_arena = torch.zeros(self._cast_end, dtype=self.fwd_dtype, device=self.device)
+            self._wbf_arena = (self._w16_arena if self.fwd_dtype == torch.bfloat16
+                               else torch.zeros(self._cast_end, dtype=torch.bfloat16, device=self.device))
+            self._bf16_versions = None
         if vers != self._bf16_versions:
-            ops.cast_bf16(self._param_arena, self._bf16_arena)
+            src = self._param_arena[:self._cast_end]
+            if self.fwd_dtype == torch.float16:
+                ops.cast_dual(src, self._w16_arena, self._wbf_arena)
+            else:
+                ops.cast_bf16(src, self._w16_arena)
             self.launches += 1
             self._bf16_versions = vers
 
@@ -466,6 +485,9 @@ class GatoPolicy(nn.Module):
         pe = self._buf("patch_emb", (plan.n_patch_rows, d), torch.float32)
         st.patch_emb = pe
         st.img_groups = []
+
+        def patches_b16(p16):  # only reached when the forward format is bf16: the kernel's fp16 rows are re-cast
+            return p16.to(torch.bfloat16)
         ie = self.image_embedding
         rb = ie.patch_embedding
         lib = load()
@@ -484,18 +506,20 @@ class GatoPolicy(nn.Module):
             n_h, n_w = g.height // self.patch_size, g.width // self.patch_size
             P = g.n_frames * n_h * n_w
             row0 = g.patch_off[0]
-            patches = self._buf(f"patches{gi}", (P, 3 * self.patch_size ** 2), torch.bfloat16)
+            patches = self._buf(f"patches{gi}", (P, 3 * self.patch_size ** 2), torch.float16)
+            patches_b = self._buf(f"patches_b{gi}", (P, 3 * self.patch_size ** 2), torch.bfloat16) if st.need_grad else None
             stats = self._buf(f"gnstats{gi}", (P, rb.num_groups, 2), torch.float32)
             check(lib.neko_patch_resblock_fwd(_p(buf), C.c_int(int(g.is_u8)), C.c_int(g.n_frames), C.c_int(g.height), C.c_int(g.width),
                                               C.c_int(self.patch_size), C.c_int(rb.mid_channels), C.c_int(rb.num_groups),
                                               _p(rb.conv1.weight), _p(rb.conv1.bias), _p(rb.gn2.weight), _p(rb.gn2.bias),
-                                              _p(rb.conv2.weight), _p(rb.conv2.bias), _p(patches), _p(stats), stream_ptr()),
+                                              _p(rb.conv2.weight), _p(rb.conv2.bias), _p(patches), _p(patches_b), _p(stats), stream_ptr()),
                   "neko_patch_resblock_fwd")
             out = pe[row0:row0 + P]
-            ops.gemm(patches, self._bview("image_embedding.post_embedding_projection.weight"), epilogue=ops.EPI_F32,
+            wproj = self._wview("image_embedding.post_embedding_projection.weight", bwd=(self.fwd_dtype != torch.float16))
+            ops.gemm(patches if wproj.dtype == torch.float16 else patches_b16(patches), wproj, epilogue=ops.EPI_F32,
                      out=out, bias=ie.post_embedding_projection.bias)
             self.launches += 2
-            st.img_groups.append((gi, g, buf, patches, stats, row0, P))
+            st.img_groups.append((gi, g, buf, patches_b, stats, row0, P))
         if st.row_bins is not None:
             bins = torch.from_numpy(np.concatenate([st.row_bins, st.col_bins]))
             dev_bins = self._buf("patch_bins", (2 * plan.n_patch_rows,), torch.int32)
@@ -559,51 +583,62 @@ class GatoPolicy(nn.Module):
         d, H = self.embed_dim, self.heads
         N = B * W
         eps = self.transformer.config.layer_norm_epsilon
+        fdt = self.fwd_dtype
+        dual = keep and fdt != torch.bfloat16   # backward GEMMs need bf16 copies of the saved activations
         acts = []
+
+        def pair(name, tag, shape):
+            """(forward-format buffer, bf16 buffer kept for backward)"""
+            if not dual:
+                t = self._buf(name + tag, shape, fdt)
+                return t, (t if keep else None)
+            return self._buf(name, shape, fdt), self._buf(name + ".b" + tag, shape, torch.bfloat16)
+
         for i, blk in enumerate(self.transformer.h):
             tag = f".{i}" if keep else ""
             pre = f"transformer.h.{i}."
-            ln1 = self._buf("ln1" + tag, (N, d), torch.bfloat16)
+            ln1, ln1_b = pair("ln1", tag, (N, d))
             m1 = self._buf("m1" + tag, (N,), torch.float32)
             r1 = self._buf("r1" + tag, (N,), torch.float32)
-            ops.layernorm_fwd(x, blk.ln_1.weight, blk.ln_1.bias, eps, ln1, m1, r1)
+            ops.layernorm_fwd(x, blk.ln_1.weight, blk.ln_1.bias, eps, ln1, m1, r1, y2=ln1_b if dual else None)
             qkv = self._buf("qkv" + tag, (N, 3 * d), torch.bfloat16)
-            ops.gemm(ln1, self._bview(pre + "attn.c_attn.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=qkv, bias=blk.attn.c_attn.bias)
-            att = self._buf("att" + tag, (N, d), torch.bfloat16)
+            ops.gemm(ln1, self._wview(pre + "attn.c_attn.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=qkv, bias=blk.attn.c_attn.bias)
+            att, att_b = pair("att", tag, (N, d))
             lse = self._buf("lse" + tag, (B, H, W), torch.float32)
-            ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse)
+            ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse,
+                              out2=att_b.view(B, W, d) if dual else None)
             x1 = self._buf(f"x.{2 * i + 1}" if keep else "x.b", (N, d), torch.float32)
-            ops.gemm(att, self._bview(pre + "attn.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x1, aux=x,
+            ops.gemm(att, self._wview(pre + "attn.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x1, aux=x,
                      bias=blk.attn.c_proj.bias)
-            ln2 = self._buf("ln2" + tag, (N, d), torch.bfloat16)
+            ln2, ln2_b = pair("ln2", tag, (N, d))
             m2 = self._buf("m2" + tag, (N,), torch.float32)
             r2 = self._buf("r2" + tag, (N,), torch.float32)
-            ops.layernorm_fwd(x1, blk.ln_2.weight, blk.ln_2.bias, eps, ln2, m2, r2)
+            ops.layernorm_fwd(x1, blk.ln_2.weight, blk.ln_2.bias, eps, ln2, m2, r2, y2=ln2_b if dual else None)
             fpre = self._buf("fpre" + tag, (N, 4 * d), torch.bfloat16)
-            fact = self._buf("fact" + tag, (N, 4 * d), torch.bfloat16)
-            ops.gemm(ln2, self._bview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
-                     bias=blk.mlp.c_fc.bias)
+            fact, fact_b = pair("fact", tag, (N, 4 * d))
+            ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
+                     out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias)
             x2 = self._buf(f"x.{2 * i + 2}" if keep else "x.a", (N, d), torch.float32)
-            ops.gemm(fact, self._bview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
+            ops.gemm(fact, self._wview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
                      bias=blk.mlp.c_proj.bias)
             self.launches += 7
             if keep:
-                acts.append((x, ln1, m1, r1, qkv, att, lse, x1, ln2, m2, r2, fpre, fact))
+                acts.append((x, ln1_b, m1, r1, qkv, att_b, lse, x1, ln2_b, m2, r2, fpre, fact_b))
             x = x2
-        hf = self._buf("hf", (N, d), torch.bfloat16)
+        hf, hf_b = pair("hf", "", (N, d))
         mf = self._buf("mf", (N,), torch.float32)
         rf = self._buf("rf", (N,), torch.float32)
-        ops.layernorm_fwd(x, self.transformer.ln_f.weight, self.transformer.ln_f.bias, eps, hf, mf, rf)
+        ops.layernorm_fwd(x, self.transformer.ln_f.weight, self.transformer.ln_f.bias, eps, hf, mf, rf, y2=hf_b if dual else None)
         self.launches += 1
         if keep:
-            st.acts, st.x_last, st.hf, st.mf, st.rf = acts, x, hf, mf, rf
+            st.acts, st.x_last, st.hf, st.mf, st.rf = acts, x, hf_b, mf, rf
         return hf
 
     def _head(self, hf: torch.Tensor, n_rows: int) -> torch.Tensor:
         """predict_token (gato_policy.py:172): fp32 logits [n_rows, Vp] (columns >= V are exact zeros).  Freshly
         allocated (torch's caching allocator) because the caller keeps the tensor."""
         logits = torch.empty(n_rows, self._Vp, dtype=torch.float32, device=self.device)
-        ops.gemm(hf, self._bview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_F32, out=logits, N=self._Vp)
+        ops.gemm(hf, self._wview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_F32, out=logits, N=self._Vp)
         self.launches += 1
         return logits
 
@@ -651,7 +686,7 @@ class GatoPolicy(nn.Module):
         else:
             logits = torch.empty(0, device=self.device)
             if st.compute_loss and n_rows:
-                hc = self._buf("hf_rows", (n_rows, d), torch.bfloat16)
+                hc = self._buf("hf_rows", (n_rows, d), self.fwd_dtype)
                 ops.gather_rows(hf, st.loss_rows, d, hc)
                 full = self._head(hc, n_rows)
                 st.logits_full, st.hf_rows = full, hc
@@ -682,7 +717,7 @@ class GatoPolicy(nn.Module):
         acc = self._begin_grads(bool(plan.n_patch_rows and getattr(st, 'img_groups', None)))
         gscale = g_loss.detach().to(torch.float32).reshape(())
         G = self._gview
-        Wb = self._bview
+        Wb = lambda n, rows=None: self._wview(n, rows, bwd=True)  # noqa: E731
 
         # ---- head + cross entropy -----------------------------------------------------------------
         compact_logits = not self.materialize_logits
@@ -692,11 +727,8 @@ class GatoPolicy(nn.Module):
                 dl.zero_()  # pad columns V..Vp must be zero (K tail of the dgrad GEMM)
             flags = ops.CE_DLOGITS_COMPACT | (ops.CE_LOGITS_COMPACT if compact_logits else 0)
             ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl, flags=flags)
-            if compact_logits:
-                hc = st.hf_rows
-            else:
-                hc = self._buf("hf_rows", (n_rows, d), torch.bfloat16)
-                ops.gather_rows(st.hf, st.loss_rows, d, hc)
+            hc = self._buf("hf_rows_b", (n_rows, d), torch.bfloat16)
+            ops.gather_rows(st.hf, st.loss_rows, d, hc)
             ops.gemm(dl, hc, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,
                      M=V, N=d, K=n_rows)
             dhc = self._buf("dhf_rows", (n_rows, d), torch.bfloat16)
@@ -793,7 +825,7 @@ class GatoPolicy(nn.Module):
             ops.gemm(gb, patches, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("image_embedding.post_embedding_projection.weight"),
                      accumulate=True, M=d, N=patches.shape[1], K=P)
             dpatch = self._buf(f"dpatches{gi}", (P, patches.shape[1]), torch.bfloat16)
-            ops.gemm(gb, self._bview("image_embedding.post_embedding_projection.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=dpatch)
+            ops.gemm(gb, self._wview("image_embedding.post_embedding_projection.weight", bwd=True), b_mn=True, epilogue=ops.EPI_BF16, out=dpatch)
             check(lib.neko_patch_resblock_bwd(_p(buf), C.c_int(int(g.is_u8)), C.c_int(g.n_frames), C.c_int(g.height), C.c_int(g.width),
                                               C.c_int(self.patch_size), C.c_int(rb.mid_channels), C.c_int(rb.num_groups),
                                               _p(rb.conv1.weight), _p(rb.conv1.bias), _p(rb.gn2.weight), _p(rb.gn2.bias),

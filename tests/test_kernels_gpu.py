@@ -102,6 +102,31 @@ def test_gemm_epilogues(ops):
     assert (out.float() - acc * p.grad).abs().max().item() < 0.1
 
 
+@pytest.mark.parametrize("a_dt,b_dt", [(torch.float16, torch.float16)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (False, True)])
+def test_gemm_fp16_operands(ops, a_dt, b_dt, a_mn, b_mn):
+    """Forward runs fp16 x fp16 (mixed f16/bf16 operands trap on tcgen05 kind::f16 and are rejected by the API)."""
+    M, N, K = 384, 512, 320
+    a_log = _rand((M, K), 61, 0.5).to(a_dt)
+    b_log = _rand((N, K), 62, 0.5).to(b_dt)
+    a = a_log.t().contiguous() if a_mn else a_log
+    b = b_log.t().contiguous() if b_mn else b_log
+    ref = a_log.float() @ b_log.float().t()
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, epilogue=ops.EPI_F32)
+    assert (out - ref).abs().max().item() < 3e-3
+    out16 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, epilogue=ops.EPI_BF16, out_dtype=torch.float16)
+    assert out16.dtype == torch.float16 and (out16.float() - ref).abs().max().item() < 0.02
+    bias = _rand((N,), 63)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    act16 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    actbf = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, epilogue=ops.EPI_GELU_BF16, out=pre, out2=act16, out3=actbf, bias=bias)
+    gref = torch.nn.functional.gelu(ref + bias)
+    assert (act16.float() - gref).abs().max().item() < 0.02 and (actbf.float() - gref).abs().max().item() < 0.08
+    with pytest.raises(Exception):
+        ops.gemm(a, b.to(torch.bfloat16), a_mn=a_mn, b_mn=b_mn)
+
+
 def test_gemm_lm_head_shape(ops):
     """K=768, N = 52305 rows of W padded to a 52352-column output (OOB rows of B zero-filled by TMA)."""
     M, K, V, Vp = 256, 768, 52305, 52352
@@ -135,11 +160,15 @@ def test_layernorm(ops, N, d):
     g = _rand((d,), 12, 0.2) + 1.0
     b = _rand((d,), 13, 0.2)
     y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5)
+    y2 = torch.empty(N, d, device="cuda", dtype=torch.bfloat16)
+    y16, _, _ = ops.layernorm_fwd(x, g, b, 1e-5, out_dtype=torch.float16, y2=y2)
+    assert torch.equal(y2, y)
     xr = x.clone().requires_grad_(True)
     gr = g.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
     ref = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5)
     assert (y.float() - ref).abs().max().item() < 0.05
+    assert y16.dtype == torch.float16 and (y16.float() - ref).abs().max().item() < 0.01
     assert (mean - x.mean(-1)).abs().max().item() < 1e-5
     dy = _rand((N, d), 14, 1.0, torch.bfloat16)
     ref.backward(dy.float())
@@ -193,6 +222,11 @@ def test_attention_fwd_bwd(ops, B, S, H, dh, S_valid):
     dout = _rand((B, S, d), 22, 1.0, torch.bfloat16) * live
     (ref * dout.float()).sum().backward()
     dqkv = ops.attention_bwd(qkv, out, dout, lse, fv, H, S_valid)
+    o2 = torch.empty_like(out)
+    out16, lse16 = ops.attention_fwd(qkv, fv, H, S_valid, out_dtype=torch.float16, out2=o2)
+    assert ((out16.float() - ref) * live).abs().max().item() < 0.03 and torch.equal(lse16, lse) and torch.equal(o2, out)
+    dqkv16 = ops.attention_bwd(qkv, out16, dout, lse, fv, H, S_valid)
+    assert (dqkv16.float() - dqkv.float()).abs().max().item() < 0.03 * max(x.grad.abs().max().item(), 1.0)
     gref = x.grad
     scale = gref.abs().max().item()
     err = (dqkv.float() - gref).abs().max().item()
