@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark: Gato training step (GatoPolicy.forward + backward + masked loss) in tokens/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+
+One "step" = one fwd+bwd pass of the hot path over one synthetic batch of the named BASELINE.json config
+(default cfg2 = configs[1]: MuJoCo 3-task control, d768 L6 H24, batch 32, k=240).  N>1: launched by torchrun,
+one rank per GPU, every rank processes its own batch (weak scaling, like the reference where every rank samples
+its own --batch_size) and gradients are all-reduced over NCCL inside backward.
+
+Rank 0 prints ONE JSON line.  `value` = tokens/s with the batch already resident in HBM (CUDA-event timed, max
+over ranks); `e2e` = the same step driven from pinned HOST tensors through the public API, with the H2D copy of
+the batch and the D2H read of the loss inside the timed region; `roofline` = tensor-core GEMM kernel (the
+dominant kernel): algorithmic FLOPs of every GEMM launch / CUDA-event time of those launches, against the
+measured bf16 peak; `cpu_baseline` = the CPU oracle port (oracle/gato_oracle.py) timed on this host's cores on
+a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+WORKLOADS = {
+    "cfg1": "GatoPolicy d128 L3 H1, HalfCheetah-shaped continuous control (obs 17, act 6), k=240, batch 4",
+    "cfg2": "MuJoCo 3-task control (halfcheetah/hopper/walker2d shapes) d768 L6 H24, k=240, batch 32/GPU",
+    "cfg3": "Atari Breakout-shaped image control (96x96 frames, 16x16 patches, ResNet patch embed) d768 L6 H24, k=512, batch 32/GPU",
+    "cfg4": "text-only GPT-2-vocab LM d768 L6 H24, 1023 ids + separator, batch 16/GPU",
+    "cfg5": "mixed multimodal batch (text + control + Atari + 224x224 caption/VQA) d768 L6 H24, k=1024, batch 32/GPU",
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gemm_flops_per_step(cfg, N, S, n_rows, head_mode, materialize):
+    """Algorithmic GEMM FLOPs actually launched on the tensor-core kernel in one fwd+bwd."""
+    d, L, V = cfg["embed_dim"], cfg["layers"], 52352
+    blocks = 3 * L * 24 * N * d * d          # 4 linears fwd + dgrad + wgrad
+    head_fwd = 2 * (N if materialize else n_rows) * d * V
+    head_bwd = 4 * (n_rows if (head_mode == "rows" or not materialize) else N) * d * V
+    return float(blocks + head_fwd + head_bwd)
+
+
+def model_flops_per_step(cfg, N, S):
+    """fwd = L(24 N d^2 + 2 N S d) + 2 N d V (attention causal-half); fwd+bwd = 3x."""
+    d, L, V = cfg["embed_dim"], cfg["layers"], 52305
+    return 3.0 * (L * (24 * N * d * d + 2 * N * S * d) + 2 * N * d * V)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port): used for cpu_baseline and for --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def cpu_oracle_tokens_per_s(config: str, sample_batch: int, steps: int, warmup: int):
+    from oracle import gato_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.GatoConfig(**O.CONFIGS[config])
+    w = O.make_weights(cfg, seed=0, perturb=False)
+    for t in w.values():
+        t.requires_grad_(True)
+    batch = O.synth_batch(config, seed=1234, batch=sample_batch)
+    tokens = int(O.tokenize(batch, cfg).token_masks.sum())
+    times = []
+    for i in range(warmup + steps):
+        for t in w.values():
+            t.grad = None
+        t0 = time.perf_counter()
+        out = O.forward(w, batch, cfg, compute_loss=True)
+        out.loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return tokens / (sum(times) / len(times)), tokens, sum(times) / len(times)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (the oracle port: /root/reference is not on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
+    tps, tokens, sec = cpu_oracle_tokens_per_s(args.config, sample, max(1, min(args.steps, 3)), 1)
+    cores = os.cpu_count() or 1
+    desc = f"fwd+bwd over {sample} samples of the {args.config} batch ({tokens} tokens) per step, fp32 torch-CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "train tokens/sec (fwd+bwd)", "value": round(tps, 2), "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOADS[args.config], "name": args.config},
+        "cpu_baseline": {"value": round(tps, 2), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(tps, 2), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def to_device(batch, dev):
+    out = []
+    for s in batch:
+        out.append({k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in s.items()})
+    return out
+
+
+def to_pinned(batch):
+    out = []
+    for s in batch:
+        d = {}
+        for k, v in s.items():
+            if isinstance(v, list):
+                v = torch.tensor(v, dtype=torch.int64)
+            d[k] = v.pin_memory() if isinstance(v, torch.Tensor) else v
+        out.append(d)
+    return out
+
+
+def batch_bytes(batch):
+    n = 0
+    for s in batch:
+        for v in s.values():
+            if isinstance(v, torch.Tensor):
+                n += v.numel() * (4 if v.dtype in (torch.int64,) else v.element_size())  # ids cross as int32
+            elif isinstance(v, list):
+                n += 4 * len(v)
+    return n
+
+
+def parse_clocks(path):
+    sm, mx, reasons = [], [], set()
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not f[0].isdigit():
+                continue
+            sm.append(float(f[1].split()[0]))
+            mx.append(float(f[2].split()[0]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+    except OSError:
+        pass
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    busy = sorted(sm)[len(sm) // 2:]  # the upper half of the samples = under load
+    return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from neko_b200 import dp, ops
+    from neko_b200.policy import GatoPolicy
+    from oracle import gato_oracle as O  # synthetic-input generator + config table only (no oracle compute on this arm)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfgd = O.CONFIGS[args.config]
+
+    class _Tok:
+        vocab_size = 50257
+
+    torch.manual_seed(0)
+    model = GatoPolicy(device=dev, embed_dim=cfgd["embed_dim"], layers=cfgd["layers"], heads=cfgd["heads"], dropout=0.0,
+                       resid_mid_channels=128, context_len=cfgd["context_len"], text_tokenizer=_Tok())
+    model.transformer.drop.p = 0.0
+    model.head_mode = args.head
+    model.materialize_logits = not args.lean
+    model.train()
+    sync = None
+    if world > 1:
+        dp.broadcast_parameters(model)
+        sync = dp.attach(model)
+    host_batch = O.synth_batch(args.config, seed=1234 + rank)
+    dev_batch = to_device(host_batch, dev)
+    pin_batch = to_pinned(host_batch)
+    tokens_per_step = int(sum(1 for _ in range(0)) or 0)
+
+    def step(batch):
+        _, loss = model(batch, compute_loss=True)
+        loss.backward()
+        return loss
+
+    # shapes of the step (host-side plan only)
+    from neko_b200.policy.packing import build_plan
+    plan = build_plan(host_batch, patch_size=16, context_len=cfgd["context_len"], pad_seq=False)
+    tokens_per_step = plan.n_valid_tokens
+    N, S, n_rows = plan.B * plan.width, plan.seq_len, int(plan.loss_rows.shape[0])
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_batch)
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
+    clk = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False)
+    smi = None
+    if rank == 0:
+        try:
+            smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader", "-lms", "100", "-i", str(local)],
+                                   stdout=clk, stderr=subprocess.DEVNULL)
+        except OSError:
+            smi = None
+    gemm_log = []
+    ops.GEMM_TIMING = gemm_log
+    l0 = model.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dev_batch)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ops.GEMM_TIMING = None
+    ms = e0.elapsed_time(e1)
+    launches = model.launches - l0
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_log)
+    gemm_fl = sum(f for _, _, f in gemm_log)
+
+    # ---- timed region 2: end to end from pinned host tensors ---------------------------------------------
+    for _ in range(2):
+        step(pin_batch).item()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record()
+    for _ in range(args.steps):
+        step(pin_batch).item()   # the D2H read of the loss closes every step
+    f1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(f0.elapsed_time(f1), wall_ms)
+    if smi is not None:
+        smi.terminate()
+        smi.wait()
+    clk.close()
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tps = tokens_per_step * world * args.steps / (ms / 1e3)
+    e2e_tps = tokens_per_step * world * args.steps / (e2e_ms / 1e3)
+    peak_tf, _hbm, peak_src = peaks()
+    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    out = {
+        "metric": "train tokens/sec (fwd+bwd)", "value": round(tps, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate + residual stream", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "name": args.config, "tokens_per_step_per_gpu": tokens_per_step,
+                   "padded_positions": N, "loss_rows": n_rows, "head": ("loss-rows only (lean)" if args.lean else f"dense logits, {args.head} backward"),
+                   "l2_policy": "per-step activations (>1.6 GB logits alone) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world}", "model_tflop_per_step_dense": round(model_flops_per_step(cfgd, N, S) / 1e12, 3)},
+        "clocks": parse_clocks(clk.name),
+        "e2e": {"value": round(e2e_tps, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(batch_bytes(host_batch) + 4096),
+                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
+                     "achieved": round(achieved, 1) if achieved else None, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": round(achieved / peak_tf, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "gemm_ms_per_step": round(gemm_ms / args.steps, 4), "gemm_share_of_step": round(gemm_ms / ms, 4),
+                     "model_flops_frac": round(model_flops_per_step(cfgd, N, S) * args.steps / (ms / 1e3) / 1e12 / peak_tf, 4)},
+    }
+    try:
+        os.unlink(clk.name)
+    except OSError:
+        pass
+    if world == 1 and not args.no_cpu_baseline:
+        sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
+        ctps, ctok, csec = cpu_oracle_tokens_per_s(args.config, sample, 2, 1)
+        out["cpu_baseline"] = {"value": round(ctps, 2), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"2 timed fwd+bwd steps over {sample} samples of the {args.config} batch ({ctok} tokens/step, "
+                                         f"{csec:.2f} s/step), fp32 torch-CPU oracle port"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--head", default="dense", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
+    ap.add_argument("--lean", action="store_true", help="evaluate the LM head on loss rows only (forward returns no logits)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -29,7 +30,8 @@ namespace neko {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
 
 struct GemmParams {
   int M, N, K;
@@ -49,6 +51,9 @@ struct GemmParams {
   long long ld_aux;
   int vec_ok;      // all epilogue pointers / leading dimensions allow 16-byte accesses
   int flags;       // NEKO_GEMM_*_F16
+  int splits;      // split-K factor (fp32 reduction into C when > 1)
+  int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
+  int kb_per_split;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -81,6 +86,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -216,7 +230,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
       const float* add = nullptr;
       if (p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16)
         add = reinterpret_cast<const float*>(p.aux) + row * p.ld_aux + col0;
-      else if (p.accumulate)
+      else if (p.accumulate && p.splits == 1)
         add = c;
       if (add) {  // read everything before the (possibly aliasing) stores below
         if (fast) {
@@ -232,7 +246,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
             if (i < ncols) f[i] += add[i];
         }
       }
-      if (fast) {
+      if (p.splits > 1) {  // split-K partial: reduce into C (pre-initialised by the host) with fp32 RED
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) atomicAdd(c + i, f[i]);
+      } else if (fast) {
         float4* c4 = reinterpret_cast<float4*>(c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) c4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -261,10 +279,137 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
 }
 
 // ---------------------------------------------------------------------------------------------
+// staged epilogue: registers -> swizzled shared-memory box (32 rows x 32 columns) -> one bulk tensor store.
+// Every global write is a full, coalesced box (TMA clips the M / N tails); accumulate and split-K use the
+// reduce-add form, so C is never read back.
+// ---------------------------------------------------------------------------------------------
+struct Stager {
+  uint8_t* base;     // this warp's two 4 KB staging buffers (1024-byte aligned), back to back
+  int which;
+  int lane;
+};
+
+__device__ __forceinline__ void stage_and_store(Stager& s, const CUtensorMap* map, const float (&f)[32], int kind /*0 f32, 1 bf16, 2 f16*/,
+                                                bool reduce, int col0, int row0) {
+  uint8_t* b = s.base + s.which * 4096;
+  s.which ^= 1;
+  if (s.lane == 0) tma_store_wait_read<1>();  // the store issued two boxes ago (same buffer) has been read out
+  __syncwarp();
+  const int r = s.lane;
+  if (kind == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<float4*>(b + r * 128 + ((c ^ (r & 7)) << 4)) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+  } else {
+    const bool h = kind == 2;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(b + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) =
+          make_uint4(pack_16x2(f[8 * c], f[8 * c + 1], h), pack_16x2(f[8 * c + 2], f[8 * c + 3], h),
+                     pack_16x2(f[8 * c + 4], f[8 * c + 5], h), pack_16x2(f[8 * c + 6], f[8 * c + 7], h));
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (s.lane == 0) {
+    if (reduce) tma_reduce_add_2d(map, smem_u32(b), col0, row0);
+    else        tma_store_2d(map, smem_u32(b), col0, row0);
+    tma_store_commit();
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stager& s, const CUtensorMap* mc, const CUtensorMap* mc2,
+                                                      const CUtensorMap* mc3, uint32_t (&v)[32], long long row, int row0, int col0,
+                                                      bool split_first) {
+  const int ncols = min(32, p.N - col0);
+  const bool in_rows = row < p.M;
+  const bool fast = (ncols == 32) && p.vec_ok;
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (p.bias && split_first) {
+    if (fast) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) f[i] += __ldg(p.bias + col0 + i);
+    }
+  }
+  const bool c_f16 = (p.flags & NEKO_GEMM_C_F16) != 0, c2_f16 = (p.flags & NEKO_GEMM_C2_F16) != 0;
+  switch (p.epi) {
+    case NEKO_EPI_BF16:
+      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      break;
+    case NEKO_EPI_GELU_BF16:
+      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+      stage_and_store(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
+      if (p.C3) stage_and_store(s, mc3, f, 1, false, col0, row0);
+      break;
+    case NEKO_EPI_DGELU_BF16: {
+      if (in_rows) {
+        const bf16* a = reinterpret_cast<const bf16*>(p.aux) + row * p.ld_aux + col0;
+        if (fast) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(a);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = a4[i];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 pre = unpack_bf16x2(w[j]);
+              f[8 * i + 2 * j] *= gelu_erf_grad(pre.x);
+              f[8 * i + 2 * j + 1] *= gelu_erf_grad(pre.y);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) f[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+        }
+      }
+      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      break;
+    }
+    case NEKO_EPI_F32:
+      stage_and_store(s, mc, f, 0, p.accumulate || p.splits > 1, col0, row0);
+      break;
+    default: {  // NEKO_EPI_RESID_F32 / NEKO_EPI_RESID_F32_BF16
+      if (in_rows) {
+        const float* add = reinterpret_cast<const float*>(p.aux) + row * p.ld_aux + col0;
+        if (fast) {
+          const float4* a4 = reinterpret_cast<const float4*>(add);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = a4[i];
+            f[4 * i] += a.x; f[4 * i + 1] += a.y; f[4 * i + 2] += a.z; f[4 * i + 3] += a.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) f[i] += add[i];
+        }
+      }
+      stage_and_store(s, mc, f, 0, false, col0, row0);
+      if (p.epi == NEKO_EPI_RESID_F32_BF16) stage_and_store(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
+      break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
+                    const __grid_constant__ CUtensorMap map_c3, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -273,7 +418,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t a_bytes = BM * BK * 2;
   const uint32_t b_bytes = (uint32_t)BN * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)stages * stage_bytes;  // 1024-byte aligned: stage_bytes is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], then the TMEM base address
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -313,16 +459,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
   const long long tiles = (long long)m_blocks * n_blocks;
+  const long long units = tiles * p.splits;  // work unit = (tile, k-split)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const long long t = u / p.splits;
+        const int ks = (int)(u - t * p.splits);
         const int m0 = (int)(t % m_blocks) * BM;
         const int n0 = (int)(t / m_blocks) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
@@ -355,11 +505,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int ks = (int)(u % p.splits);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -370,7 +522,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // MN-major: step 16 k-rows = two 8-row swizzle atoms = 2048 bytes.
             const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 2048, BK * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));  // ring slot free once these MMAs have read it
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -382,9 +534,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    Stager stg;
+    stg.base = staging + (size_t)q * 8192;
+    stg.which = 0;
+    stg.lane = lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long t = u / p.splits;
+      const bool split_first = (u - t * p.splits) == 0;
       const int m0 = (int)(t % m_blocks) * BM;
       const int n0 = (int)(t / m_blocks) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -396,13 +554,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tc_ld32(taddr + (uint32_t)(c * 32), v);
-        if (row < p.M) epilogue_chunk(p, v, row, col0);
+        if (p.tma_store) epilogue_chunk_staged(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
+        else if (row < p.M) epilogue_chunk(p, v, row, col0);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();  // staging buffers must outlive their bulk reads
   }
 
   tc_fence_before();
@@ -437,7 +597,7 @@ struct MapKey {
   const void* ptr;
   unsigned long long inner, outer, ld;
   unsigned box_inner, box_outer;
-  int f16;
+  int f16;  // 0 bf16, 1 f16 (operands, 128B swizzle); 2 f32 output box (128B swizzle); 3 / 4 bf16 / f16 output box (64B swizzle)
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && f16 == o.f16;
   }
@@ -465,11 +625,15 @@ static int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner,
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return NEKO_ECUDA; }
   const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {ld * 2ull};
+  const unsigned long long esz = (f16 == 2) ? 4ull : 2ull;
+  const cuuint64_t strides[1] = {ld * esz};
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapDataType dt = (f16 == 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : ((f16 == 1 || f16 == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const CUtensorMapSwizzle sw = (f16 >= 3) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr, inner, outer, ld, box_inner, box_outer);
@@ -512,17 +676,38 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.epi = epilogue; p.accumulate = accumulate; p.flags = flags;
   p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.C3 = C3; p.ldc3 = ldc3; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
-  // wide tiles when there are enough of them to fill the machine
+  // tile width and split-K factor: minimise  waves x (main loop + epilogue)  in units of one 128-wide k-block.
+  // The narrow tile pays ~15% more operand traffic per flop; the epilogue of a tile costs about 3 k-blocks per
+  // 128 columns.  Split-K (fp32 RED into C) is only used for plain fp32 outputs: the weight gradients, whose M x N
+  // is a handful of tiles while K is the whole token axis.
   const int sms = sm_count();
-  // tile width: fewest (waves x tile time); the narrow tile pays ~15% more operand traffic per flop
   const long long mb_ = (M + BM - 1) / BM;
-  const long long tiles128 = mb_ * ((N + 127) / 128), tiles256 = mb_ * ((N + 255) / 256);
-  const double cost128 = 1.15 * (double)((tiles128 + sms - 1) / sms);
-  const double cost256 = 2.0 * (double)((tiles256 + sms - 1) / sms);
-  p.BN = (N > 128 && cost256 <= cost128) ? 256 : 128;
+  const int kblocks = (K + BK - 1) / BK;
+  const bool can_split = (epilogue == NEKO_EPI_F32) && (bias == nullptr);
+  double best = 1e30;
+  p.BN = 128; p.splits = 1;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    if (bn == 256 && N <= 128) break;
+    const long long tiles_ = mb_ * ((N + bn - 1) / bn);
+    for (int sp = 1; sp <= (can_split ? 16 : 1); ++sp) {
+      if (sp > 1 && kblocks / sp < 8) break;
+      const long long units_ = tiles_ * sp;
+      const double per_unit = ((kblocks + sp - 1) / sp) * (bn == 128 ? 1.15 : 2.0) + 3.0 * (bn / 128) * (sp > 1 ? 1.5 : 1.0);
+      const double cost = (double)((units_ + sms - 1) / sms) * per_unit;
+      if (cost < best - 1e-9) { best = cost; p.BN = bn; p.splits = sp; }
+    }
+  }
   if (const char* force = getenv("NEKO_GEMM_BN")) { const int v = atoi(force); if (v == 128 || v == 256) p.BN = v; }
+  if (const char* force = getenv("NEKO_GEMM_SPLITS")) { const int v = atoi(force); if (v >= 1 && can_split) p.splits = v; }
+  p.kb_per_split = (kblocks + p.splits - 1) / p.splits;
+  p.splits = (kblocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  if (p.splits > 1 && !accumulate) {  // (also correct for the reduce-add TMA path)
+    // partial sums are RED-added: start from zero
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, as_stream(stream));
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(gemm split-K)");
+  }
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  p.stages = (SMEM_BUDGET - 1024 - 256) / stage_bytes;
+  p.stages = (SMEM_BUDGET - 1024 - 256 - STAGING_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   const bool out_bf16 = (epilogue == NEKO_EPI_BF16 || epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_DGELU_BF16);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -533,25 +718,44 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   if (aux) vec = vec && al16(aux) && (ld_aux % (epilogue == NEKO_EPI_DGELU_BF16 ? 8 : 4) == 0);
   p.vec_ok = vec ? 1 : 0;
 
-  CUtensorMap ma, mb;
+  // outputs through TMA when every output tensor is 16-byte aligned with a 16-byte-multiple pitch
+  auto tma_ok = [&](const void* q, long long ld, int esz) { return q == nullptr || (al16(q) && (ld * esz) % 16 == 0); };
+  const int c_esz = out_bf16 ? 2 : 4;
+  p.tma_store = (tma_ok(C, ldc, c_esz) && tma_ok(C2, ldc2, 2) && tma_ok(C3, ldc3, 2)) ? 1 : 0;
+  if (getenv("NEKO_GEMM_DIRECT_STORE")) p.tma_store = 0;
+  CUtensorMap ma, mb, mc, mc2, mc3;
+  memset(&mc, 0, sizeof(mc)); memset(&mc2, 0, sizeof(mc2)); memset(&mc3, 0, sizeof(mc3));
   int rc;
-  if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM, flags & NEKO_GEMM_A_F16);
-  else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK, flags & NEKO_GEMM_A_F16);
+  if (p.tma_store) {
+    const int ckind = out_bf16 ? ((flags & NEKO_GEMM_C_F16) ? 4 : 3) : 2;
+    rc = make_map(&mc, C, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ldc, 32, 32, ckind);
+    if (rc != NEKO_OK) return rc;
+    if (C2) {
+      rc = make_map(&mc2, C2, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ldc2, 32, 32, (flags & NEKO_GEMM_C2_F16) ? 4 : 3);
+      if (rc != NEKO_OK) return rc;
+    }
+    if (C3) {
+      rc = make_map(&mc3, C3, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ldc3, 32, 32, 3);
+      if (rc != NEKO_OK) return rc;
+    }
+  }
+  if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
+  else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
-  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN, flags & NEKO_GEMM_B_F16);
-  else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK, flags & NEKO_GEMM_B_F16);
+  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
+  else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
 
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)p.stages * stage_bytes + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, p);
+  const long long units = (long long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN) * p.splits;
+  const int grid = (int)(units < sms ? units : sms);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, mc, mc2, mc3, p);
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return NEKO_OK;
 }

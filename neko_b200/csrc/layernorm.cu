@@ -62,9 +62,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-// Each CTA owns `rows_per_cta` consecutive rows; warps stride over them.  dgamma / dbeta partials are
-// kept per lane in registers, reduced across the CTA's warps through shared memory, then one
-// atomicAdd per column per CTA.
+// Each CTA owns `rows_per_cta` consecutive rows; warps stride over them.  The row lives in registers (x and dy
+// only: xhat and gamma*dy are recomputed in the second pass to keep the register count, hence the occupancy of
+// this pure streaming kernel, reasonable).  dgamma / dbeta partials go to shared-memory accumulators (RED.shared),
+// then one global atomicAdd per column per CTA.
 template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -78,13 +79,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   const int nv = d >> 2;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) smem[i] = 0.f;
   __syncthreads();
-
-  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
-#pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; ++k) {
-    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(N, row0 + rows_per_cta);
@@ -92,56 +86,51 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
     const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * d);
     const uint2* dy2 = reinterpret_cast<const uint2*>(dy + (size_t)row * d);
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_MAX_VEC], gy[LN_MAX_VEC];
+    float4 xv[LN_MAX_VEC];
+    uint2 dv[LN_MAX_VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < LN_MAX_VEC; ++k) {
       const int i = lane + k * 32;
       if (i < nv) {
-        const float4 xv = x4[i];
-        const uint2 dv = dy2[i];
-        const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+        xv[k] = x4[i];
+        dv[k] = dy2[i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+      const int i = lane + k * 32;
+      if (i < nv) {
+        const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
         const float4 g = __ldg(g4 + i);
-        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        ab[k].x += d01.x; ab[k].y += d01.y; ab[k].z += d23.x; ab[k].w += d23.y;
-        ag[k].x += d01.x * xh[k].x; ag[k].y += d01.y * xh[k].y; ag[k].z += d23.x * xh[k].z; ag[k].w += d23.y * xh[k].w;
-        gy[k] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
-        s1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
-        s2 += (gy[k].x * xh[k].x + gy[k].y * xh[k].y) + (gy[k].z * xh[k].z + gy[k].w * xh[k].w);
+        const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * (xv[k].x - mu) + g1 * (xv[k].y - mu)) + (g2 * (xv[k].z - mu) + g3 * (xv[k].w - mu));
       }
     }
     s1 = warp_sum(s1) / (float)d;
-    s2 = warp_sum(s2) / (float)d;
+    s2 = warp_sum(s2) * rs / (float)d;
     float4* r4 = reinterpret_cast<float4*>(dx_resid + (size_t)row * d);
     uint2* o2 = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * d) : nullptr;
 #pragma unroll
     for (int k = 0; k < LN_MAX_VEC; ++k) {
       const int i = lane + k * 32;
       if (i < nv) {
+        const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
+        const float4 g = __ldg(g4 + i);
+        const float h0 = (xv[k].x - mu) * rs, h1 = (xv[k].y - mu) * rs, h2 = (xv[k].z - mu) * rs, h3 = (xv[k].w - mu) * rs;
         float4 r = r4[i];
-        r.x += rs * (gy[k].x - s1 - xh[k].x * s2);
-        r.y += rs * (gy[k].y - s1 - xh[k].y * s2);
-        r.z += rs * (gy[k].z - s1 - xh[k].z * s2);
-        r.w += rs * (gy[k].w - s1 - xh[k].w * s2);
+        r.x += rs * (d01.x * g.x - s1 - h0 * s2);
+        r.y += rs * (d01.y * g.y - s1 - h1 * s2);
+        r.z += rs * (d23.x * g.z - s1 - h2 * s2);
+        r.w += rs * (d23.y * g.w - s1 - h3 * s2);
         r4[i] = r;
-        if (o2) {
-          uint2 o;
-          o.x = pack_bf16x2(r.x, r.y);
-          o.y = pack_bf16x2(r.z, r.w);
-          o2[i] = o;
-        }
+        if (o2) o2[i] = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+        float* sg = smem + 4 * i;
+        float* sb = smem + d + 4 * i;
+        atomicAdd(sg + 0, d01.x * h0); atomicAdd(sg + 1, d01.y * h1); atomicAdd(sg + 2, d23.x * h2); atomicAdd(sg + 3, d23.y * h3);
+        atomicAdd(sb + 0, d01.x); atomicAdd(sb + 1, d01.y); atomicAdd(sb + 2, d23.x); atomicAdd(sb + 3, d23.y);
       }
-    }
-  }
-  // CTA-level reduction of the affine gradients
-#pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; ++k) {
-    const int i = lane + k * 32;
-    if (i < nv) {
-      float* sg = smem + 4 * i;
-      float* sb = smem + d + 4 * i;
-      atomicAdd(sg + 0, ag[k].x); atomicAdd(sg + 1, ag[k].y); atomicAdd(sg + 2, ag[k].z); atomicAdd(sg + 3, ag[k].w);
-      atomicAdd(sb + 0, ab[k].x); atomicAdd(sb + 1, ab[k].y); atomicAdd(sb + 2, ab[k].z); atomicAdd(sb + 3, ab[k].w);
     }
   }
   __syncthreads();
@@ -177,8 +166,8 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
   NEKO_REQUIRE(dy_bf16 && x && gamma && mean && rstd && dx_resid && dgamma && dbeta, "layernorm_bwd: null pointer");
   NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_bwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
   const int threads = 256;
-  // ~4 CTAs per SM, each a contiguous row range
-  int ctas = sm_count() * 4;
+  // ~8 CTAs per SM, each a contiguous row range
+  int ctas = sm_count() * 8;
   int rows_per_cta = (N + ctas - 1) / ctas;
   if (rows_per_cta < 8) rows_per_cta = 8;
   ctas = (N + rows_per_cta - 1) / rows_per_cta;

@@ -17,6 +17,7 @@ from ._lib import (EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F
 
 _16BIT = (torch.bfloat16, torch.float16)
 GEMM_A_F16, GEMM_B_F16, GEMM_C_F16, GEMM_C2_F16 = 1, 2, 4, 8
+GEMM_TIMING = None  # list collecting (start_event, end_event, flops) per launch when set by bench.py
 
 
 def _cuda(*ts):
@@ -64,7 +65,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                   C2=_ptr(out2), ldc2=out2.stride(0) if out2 is not None else 0,
                   C3=_ptr(out3), ldc3=out3.stride(0) if out3 is not None else 0,
                   bias=_ptr(bias), aux=_ptr(aux), ld_aux=aux.stride(0) if aux is not None else 0)
-    check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
+    if GEMM_TIMING is not None:  # bench.py: CUDA events around every tensor-core launch (roofline.achieved)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
+        e1.record()
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K))
+    else:
+        check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
     if out2 is not None and epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16):
         return out, out2
     return out

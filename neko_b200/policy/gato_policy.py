@@ -714,6 +714,9 @@ class GatoPolicy(nn.Module):
         B, W, d, V, Vp, H = plan.B, plan.width, self.embed_dim, self.vocab_size, self._Vp, self.heads
         N = B * W
         n_rows = st.n_rows
+        sync = getattr(self, "_grad_sync", None)
+        if sync is not None:
+            sync.begin_step()
         acc = self._begin_grads(bool(plan.n_patch_rows and getattr(st, 'img_groups', None)))
         gscale = g_loss.detach().to(torch.float32).reshape(())
         G = self._gview
@@ -755,6 +758,7 @@ class GatoPolicy(nn.Module):
         lnf = self.transformer.ln_f
         ops.layernorm_bwd(dhf, st.x_last, lnf.weight, st.mf, st.rf, dx, G("transformer.ln_f.weight"), G("transformer.ln_f.bias"), dxb)
         self.launches += 2
+        self._notify("transformer.ln_f.weight", "transformer.ln_f.bias")
 
         # ---- blocks, last to first ------------------------------------------------------------------------
         for i in reversed(range(self.layers)):
@@ -802,7 +806,10 @@ class GatoPolicy(nn.Module):
         self.launches += 1
         if dpe is not None:
             self._image_backward(st, dpe, acc)
-        self._notify("pos_embed_observation.weight", self._order[-1])
+        first_tail = next(n for n in self._order if n.startswith("image_embedding.") or n == "pos_embed_observation.weight")
+        self._notify(first_tail, self._order[-1])
+        if sync is not None:
+            sync.finish()
 
     def _image_backward(self, st: _State, dpe: torch.Tensor, acc: bool):
         d = self.embed_dim

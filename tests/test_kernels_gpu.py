@@ -63,6 +63,21 @@ def test_gemm_layouts(ops, M, N, K, a_mn, b_mn):
     assert err < tol, f"max err {err} (tol {tol})"
 
 
+@pytest.mark.parametrize("M,N,K", [(768, 768, 7680), (768, 3072, 7680), (768, 2304, 4000), (3072, 768, 15808), (256, 128, 2048)])
+def test_gemm_split_k_weight_gradients(ops, M, N, K):
+    """wgrad shape: few output tiles, K = the token axis -> split-K with fp32 RED reduction, both overwrite and
+    accumulate semantics."""
+    x = _rand((K, M), 71, 0.5, torch.bfloat16)   # activations [tokens, in]
+    dy = _rand((K, N), 72, 0.5, torch.bfloat16)  # gradients  [tokens, out]
+    ref = x.float().t() @ dy.float()
+    out = torch.full((M, N), 7.0, device="cuda")
+    ops.gemm(x, dy, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=out)
+    tol = 2e-3 * math.sqrt(K / 64) + 1e-4
+    assert (out - ref).abs().max().item() < tol
+    ops.gemm(x, dy, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=out, accumulate=True)
+    assert (out - 2 * ref).abs().max().item() < 2 * tol
+
+
 def test_gemm_epilogues(ops):
     M, N, K = 384, 256, 192
     a = _rand((M, K), 3, 0.5, torch.bfloat16)

@@ -1,0 +1,34 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, total and share.
+Only the LAST step is counted when a step marker (tokenize_embed_kernel) is present."""
+import csv
+import sys
+from collections import OrderedDict
+
+rows = []
+with open(sys.argv[1], newline="") as f:
+    lines = [ln for ln in f if not ln.startswith("==")]
+for r in csv.DictReader(lines):
+    if r.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    val = float(r["Metric Value"].replace(",", ""))
+    unit = r.get("Metric Unit", "ns")
+    ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(unit, 1)
+    rows.append((r["Kernel Name"], ns))
+# keep the launches of the last step
+starts = [i for i, (k, _) in enumerate(rows) if "tokenize_embed" in k]
+if len(starts) >= 2:
+    # the cast of the weights precedes tokenize; include it
+    s = starts[-1]
+    while s > 0 and ("cast_f32" in rows[s - 1][0]):
+        s -= 1
+    rows = rows[s:]
+agg = OrderedDict()
+for k, ns in rows:
+    name = k.split("(")[0]
+    c, t = agg.get(name, (0, 0.0))
+    agg[name] = (c + 1, t + ns)
+total = sum(t for _, t in agg.values())
+print(f"launches in one step: {len(rows)}   summed device time: {total / 1e6:.3f} ms (ncu-serialised, cold cache)")
+print(f"{'kernel':60s} {'count':>6s} {'ms':>9s} {'share':>7s}")
+for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{name[:60]:60s} {c:6d} {t / 1e6:9.3f} {100 * t / total:6.1f}%")
