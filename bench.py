@@ -237,8 +237,17 @@ def run_ours(args):
     ops.GEMM_TIMING = None
     ms = e0.elapsed_time(e1)
     launches = model.launches - l0
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_log)
-    gemm_fl = sum(f for _, _, f in gemm_log)
+    gemm_ms = sum(g[0].elapsed_time(g[1]) for g in gemm_log)
+    gemm_fl = sum(g[2] for g in gemm_log)
+    if args.gemm_report and rank == 0:
+        agg = {}
+        for g in gemm_log:
+            c, t = agg.get(g[3], (0, 0.0))
+            agg[g[3]] = (c + 1, t + g[0].elapsed_time(g[1]))
+        print("GEMM report (M, N, K, a_mn, b_mn, epilogue): launches/step, avg us, TFLOP/s", file=sys.stderr)
+        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            us = t / c * 1e3
+            print(f"  {str(k):44s} {c // args.steps:3d} {us:9.1f} {2.0 * k[0] * k[1] * k[2] / us / 1e6:8.1f}  total/step {t / args.steps:7.3f} ms", file=sys.stderr)
 
     # ---- timed region 2: end to end from pinned host tensors ---------------------------------------------
     for _ in range(2):
@@ -316,6 +325,7 @@ def main():
     ap.add_argument("--head", default="dense", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
     ap.add_argument("--lean", action="store_true", help="evaluate the LM head on loss rows only (forward returns no logits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-report", action="store_true", help="per-shape GEMM timings (CUDA events) on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -44,11 +44,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): one rcp, one ex2, a degree-5 Horner chain -- a
+// fraction of libdevice erff(); well below the rounding of the 16-bit outputs it feeds.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float a = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));  // MUFU.RCP, ~1 ulp
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = 1.0f - p * t * __expf(-a * a);
+  return copysignf(y, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }

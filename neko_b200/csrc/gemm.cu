@@ -29,9 +29,11 @@ namespace neko {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+constexpr int STAGING_PER_WARP = 8192;  // ring of 2 fp32 boxes (32 rows x 128 B) or 4 16-bit boxes (32 rows x 64 B)
+constexpr int STAGING_BYTES = GEMM_EPI_WARPS * STAGING_PER_WARP;
 
 struct GemmParams {
   int M, N, K;
@@ -52,6 +54,7 @@ struct GemmParams {
   int vec_ok;      // all epilogue pointers / leading dimensions allow 16-byte accesses
   int flags;       // NEKO_GEMM_*_F16
   int splits;      // split-K factor (fp32 reduction into C when > 1)
+  int n_fast;      // tile rasterisation: consecutive work units walk N first (else M first)
   int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
   int kb_per_split;
 };
@@ -284,16 +287,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
 // reduce-add form, so C is never read back.
 // ---------------------------------------------------------------------------------------------
 struct Stager {
-  uint8_t* base;     // this warp's two 4 KB staging buffers (1024-byte aligned), back to back
-  int which;
+  uint8_t* base;     // this warp's 8 KB staging ring (1024-byte aligned)
   int lane;
+  int slot;          // next ring slot
+  int wide;          // 1: 4 KB slots (some output of this epilogue is fp32), 0: 2 KB slots (all outputs 16-bit)
 };
 
 __device__ __forceinline__ void stage_and_store(Stager& s, const CUtensorMap* map, const float (&f)[32], int kind /*0 f32, 1 bf16, 2 f16*/,
                                                 bool reduce, int col0, int row0) {
-  uint8_t* b = s.base + s.which * 4096;
-  s.which ^= 1;
-  if (s.lane == 0) tma_store_wait_read<1>();  // the store issued two boxes ago (same buffer) has been read out
+  // ring of staging slots: before overwriting a slot, the bulk store that last used it must have read it out,
+  // i.e. at most (slots - 1) younger stores may still be pending
+  uint8_t* b;
+  if (s.wide) {
+    b = s.base + (s.slot << 12);
+    s.slot = (s.slot + 1) & 1;
+    if (s.lane == 0) tma_store_wait_read<1>();
+  } else {
+    b = s.base + (s.slot << 11);
+    s.slot = (s.slot + 1) & 3;
+    if (s.lane == 0) tma_store_wait_read<3>();
+  }
   __syncwarp();
   const int r = s.lane;
   if (kind == 0) {
@@ -441,7 +454,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -469,8 +482,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (long long u = blockIdx.x; u < units; u += gridDim.x) {
         const long long t = u / p.splits;
         const int ks = (int)(u - t * p.splits);
-        const int m0 = (int)(t % m_blocks) * BM;
-        const int n0 = (int)(t / m_blocks) * BN;
+        const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * BM;
+        const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -535,21 +548,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     Stager stg;
-    stg.base = staging + (size_t)q * 8192;
-    stg.which = 0;
+    const int e = warp - 2;            // 0..7
+    const int half = e >> 2;           // which half of the tile's columns
+    stg.base = staging + (size_t)e * STAGING_PER_WARP;
     stg.lane = lane;
+    stg.slot = 0;
+    stg.wide = (p.epi == NEKO_EPI_F32 || p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16) ? 1 : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       const long long t = u / p.splits;
       const bool split_first = (u - t * p.splits) == 0;
-      const int m0 = (int)(t % m_blocks) * BM;
-      const int n0 = (int)(t / m_blocks) * BN;
+      const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * BM;
+      const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const long long row = (long long)m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
@@ -699,6 +716,11 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   }
   if (const char* force = getenv("NEKO_GEMM_BN")) { const int v = atoi(force); if (v == 128 || v == 256) p.BN = v; }
   if (const char* force = getenv("NEKO_GEMM_SPLITS")) { const int v = atoi(force); if (v >= 1 && can_split) p.splits = v; }
+  // rasterisation: the operand that is re-read across the concurrently running tiles should be the small one --
+  // walk the shorter block dimension fastest so one wave covers a squarish patch of C and the long operand streams
+  // from HBM exactly once (head dgrad / wgrad: 800 MB of dlogits)
+  p.n_fast = (((N + p.BN - 1) / p.BN) < mb_) ? 1 : 0;
+  if (const char* force = getenv("NEKO_GEMM_NFAST")) p.n_fast = atoi(force) ? 1 : 0;
   p.kb_per_split = (kblocks + p.splits - 1) / p.splits;
   p.splits = (kblocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   if (p.splits > 1 && !accumulate) {  // (also correct for the reduce-add TMA path)

@@ -166,8 +166,9 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
   NEKO_REQUIRE(dy_bf16 && x && gamma && mean && rstd && dx_resid && dgamma && dbeta, "layernorm_bwd: null pointer");
   NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_bwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
   const int threads = 256;
-  // ~8 CTAs per SM, each a contiguous row range
-  int ctas = sm_count() * 8;
+  // one resident wave (2 CTAs per SM at ~100 registers), each CTA a contiguous row range: few CTAs keep the
+  // final global atomics (2*d per CTA, all on the same 2*d addresses) cheap
+  int ctas = sm_count() * 2;
   int rows_per_cta = (N + ctas - 1) / ctas;
   if (rows_per_cta < 8) rows_per_cta = 8;
   ctas = (N + rows_per_cta - 1) / rows_per_cta;

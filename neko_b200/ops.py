@@ -70,7 +70,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         e0.record()
         check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
         e1.record()
-        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K))
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), epilogue)))
     else:
         check(load().neko_gemm(C.byref(gd), stream_ptr()), "neko_gemm")
     if out2 is not None and epilogue in (EPI_GELU_BF16, EPI_RESID_F32_BF16):

@@ -746,9 +746,12 @@ class GatoPolicy(nn.Module):
             ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl)
             ops.gemm(dl, st.hf, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,
                      M=V, N=d, K=N)
+            # K = the padded vocabulary (818 k-blocks) but only 360 output tiles: fp32 output lets the kernel split K
+            dhf32 = self._buf("dhf_f32", (N, d), torch.float32)
+            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_F32, out=dhf32, M=N, N=d, K=Vp)
             dhf = self._buf("dhf", (N, d), torch.bfloat16)
-            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_BF16, out=dhf, M=N, N=d, K=Vp)
-            self.launches += 4
+            ops.cast_bf16(dhf32, dhf)
+            self.launches += 6
         self._notify("predict_token.weight", "predict_token.weight")
 
         # ---- ln_f -------------------------------------------------------------------------------------

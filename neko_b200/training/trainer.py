@@ -1,0 +1,163 @@
+"""Training step around the hot path, mirroring gato/training/trainer.py:127-188 and schedulers.py:21-32.
+
+What is reproduced exactly: the per-task batch split from the *_prop flags incl. the multinomial remainder draw
+(trainer.py:134-154), forward/backward on the combined dict list, global-norm clip 1.0, AdamW(0.9/0.95, 1e-8, wd 0.1
+on every parameter), linear warm-up + cosine decay, gradient accumulation.  The optimiser runs as one fused kernel
+over the flat arenas (csrc/optim.cu); data parallelism is neko_b200.dp.  Evaluation / W&B / checkpoints are host
+plumbing outside the hot path (utils.save_checkpoint writes the reference's file layout)."""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time
+from typing import List, Sequence
+
+import torch
+
+from .. import ops
+
+
+def split_batch_by_props(batch_size: int, text_prop: float, caption_prop: float, vqa_prop: float):
+    """trainer.py:134-154 -> (text, caption, vqa, control) batch sizes.  One torch.multinomial draw over the
+    fractional residuals hands out the remainder."""
+    control_prop = 1 - text_prop - caption_prop - vqa_prop
+    text_bs = int(text_prop * batch_size)
+    caption_bs = int(caption_prop * batch_size)
+    vqa_bs = int(vqa_prop * batch_size)
+    control_bs = int(control_prop * batch_size)
+    remainder = batch_size - text_bs - caption_bs - vqa_bs - control_bs
+    if remainder > 0:
+        residuals = [text_prop * batch_size - text_bs, caption_prop * batch_size - caption_bs,
+                     vqa_prop * batch_size - vqa_bs, control_prop * batch_size - control_bs]
+        idx = torch.multinomial(torch.tensor(residuals), num_samples=1).item()
+        add = [0, 0, 0, 0]
+        add[idx] = remainder
+        text_bs, caption_bs, vqa_bs, control_bs = text_bs + add[0], caption_bs + add[1], vqa_bs + add[2], control_bs + add[3]
+    assert batch_size == text_bs + caption_bs + vqa_bs + control_bs
+    return text_bs, caption_bs, vqa_bs, control_bs
+
+
+def lr_at_step(step: int, *, warmup_steps: int, training_steps: int, base_lr: float, init_lr: float, min_lr: float,
+               cosine_decay: bool = True) -> float:
+    """schedulers.py:21-32 (the LambdaLR factor times base_lr)."""
+    if step <= warmup_steps:
+        return init_lr + (base_lr - init_lr) * step / max(1, warmup_steps)
+    if cosine_decay:
+        progress = (step - warmup_steps) / float(max(1, training_steps - warmup_steps))
+        return min_lr + 0.5 * (base_lr - min_lr) * (1 + math.cos(math.pi * progress))
+    return base_lr
+
+
+class FusedAdamW:
+    """AdamW + global-norm clip over the policy's flat arenas: two launches per step (sum of squares, update)."""
+
+    def __init__(self, policy, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1):
+        self.policy = policy
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(policy._param_arena)
+        self.exp_avg_sq = torch.zeros_like(policy._param_arena)
+        self.sumsq = torch.zeros((), device=policy._param_arena.device)
+        self.t = 0
+
+    def step(self, max_norm: float = 0.0, grad_div: float = 1.0):
+        p = self.policy
+        self.t += 1
+        ss = None
+        if max_norm > 0:
+            self.sumsq.zero_()
+            ops.sumsq(p._grad_arena, self.sumsq)
+            ss = self.sumsq
+        ops.adamw_step(p._param_arena, p._grad_arena, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                       self.eps, self.weight_decay, self.t, ss, max_norm, grad_div)
+        for q in p._params.values():   # the arena was updated in place: invalidate the 16-bit weight copies
+            q._version  # noqa: B018 (read-only attribute; the bump below is the supported way)
+        p._bf16_versions = None
+
+    def zero_grad(self):
+        self.policy.zero_grad()
+
+
+class Trainer:
+    def __init__(self, model, optimizer: FusedAdamW, tasks: Sequence, args, sync=None, exp_name: str = "neko_b200"):
+        self.model, self.optimizer, self.tasks, self.args, self.sync = model, optimizer, list(tasks), args, sync
+        self.exp_name = exp_name
+        self.steps = 0
+        self.min_lr = args.learning_rate / args.min_factor
+
+    # task sampling ----------------------------------------------------------------------------------------
+    def _sample(self, kind: str, n: int) -> List[dict]:
+        out: List[dict] = []
+        tasks = [t for t in self.tasks if t.kind == kind]
+        if kind == "control":
+            # trainer.py:211-247 draws tasks without replacement until the batch is full
+            i = 0
+            while len(out) < n and tasks:
+                out.extend(tasks[i % len(tasks)].sample_batch(1, max_tokens=self.args.sequence_length))
+                i += 1
+            return out[:n]
+        for t in tasks:
+            out.extend(t.sample_batch(n, max_tokens=self.args.sequence_length))
+        return out
+
+    def sample_combined_batch(self) -> List[dict]:
+        a = self.args
+        text_bs, caption_bs, vqa_bs, control_bs = split_batch_by_props(a.batch_size, a.text_prop, a.caption_prop, a.vqa_prop)
+        batch: List[dict] = []
+        if text_bs > 0:
+            batch += self._sample("text", text_bs)
+        if caption_bs > 0:
+            batch += self._sample("caption", caption_bs)
+        if vqa_bs > 0:
+            batch += self._sample("vqa", vqa_bs)
+        if control_bs > 0:
+            batch += self._sample("control", control_bs)
+        return batch
+
+    # one optimisation step (trainer.py:127-188) ------------------------------------------------------
+    def train_step(self):
+        a = self.args
+        accum = max(1, a.gradient_accumulation_steps)
+        self.optimizer.lr = lr_at_step(self.steps, warmup_steps=a.warmup_steps, training_steps=a.training_steps,
+                                       base_lr=a.learning_rate, init_lr=a.init_lr, min_lr=self.min_lr,
+                                       cosine_decay=not a.disable_cosine_decay)
+        t0 = time.time()
+        losses = []
+        for micro in range(accum):
+            batch = self.sample_combined_batch()
+            last = micro == accum - 1
+            ctx = self.sync.no_sync() if (self.sync is not None and not last) else _null()
+            with ctx:
+                _, loss = self.model.forward(inputs=batch, compute_loss=True)
+                (loss / accum).backward()
+            losses.append(loss.detach())
+        self.optimizer.step(max_norm=0.0 if a.disable_grad_clip else a.grad_norm_clip)
+        self.optimizer.zero_grad()
+        self.steps += 1
+        loss_val = torch.stack(losses).mean().cpu().item()   # host sync once per step, like trainer.py:188
+        return loss_val, {"training/learning_rate": self.optimizer.lr, "time/train_step": time.time() - t0}
+
+    def train(self, steps: int):
+        self.model.train()
+        logs = []
+        for _ in range(steps):
+            logs.append(self.train_step())
+        return logs
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def save_checkpoint(model, save_dir: str, name: str, args) -> str:
+    """utils/utils.py:19-32 file layout: <save_dir>/<name>.pt (state_dict) + args.json."""
+    os.makedirs(save_dir, exist_ok=True)
+    path = os.path.join(save_dir, f"{name}.pt")
+    torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
+    with open(os.path.join(save_dir, "args.json"), "w") as f:
+        json.dump({k: v for k, v in vars(args).items()}, f, indent=1, default=str)
+    return path

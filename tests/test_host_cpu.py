@@ -1,0 +1,147 @@
+"""CPU-side tests (no GPU): C-ABI library loads and exports every declared symbol, host batch planning agrees
+with the oracle, the reference-facing error behaviour of the planner, and the data-parallel bucket logic over
+gloo with world_size 2."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gato_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from neko_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from neko_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 25 and "neko_gemm" in names and "neko_tokenize_embed_fwd" in names
+    lib = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/neko_b200.h but not exported"
+    assert _lib.load().neko_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from neko_b200._lib import GemmDesc, SampleDesc, TokParams
+    assert ctypes.sizeof(SampleDesc) == 64
+    assert ctypes.sizeof(TokParams) == 40
+    assert ctypes.sizeof(GemmDesc) == 8 * 4 + 13 * 8
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device (no oracle / CPU route)."""
+    from neko_b200.policy import GatoPolicy
+    with pytest.raises(Exception):
+        GatoPolicy(device="cpu", embed_dim=64, layers=1, heads=2, dropout=0.0, resid_mid_channels=128)
+    import neko_b200.policy.gato_policy as gp
+    import neko_b200.ops as ops_mod
+    for mod in (gp, ops_mod):
+        src = open(mod.__file__).read()
+        assert "import oracle" not in src and "from oracle" not in src, "product code must not import the oracle"
+    if not torch.cuda.is_available():
+        from neko_b200 import ops
+        with pytest.raises(Exception):
+            ops.cast_bf16(torch.zeros(8))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_plan_matches_oracle_masks(name):
+    from neko_b200.policy.packing import build_plan
+    cfg = O.GatoConfig(context_len=O.CONFIGS[name]["context_len"])
+    batch = O.synth_batch(name)
+    tb = O.tokenize(batch, cfg)
+    plan = build_plan(batch, patch_size=16, context_len=cfg.context_len, pad_seq=False)
+    B, S = tb.tokens.shape
+    assert (plan.B, plan.seq_len, plan.width) == (B, S, S)
+    rows = (np.arange(B)[:, None] * S + np.arange(S - 1)[None, :])[tb.loss_mask > 0]
+    assert np.array_equal(np.sort(plan.loss_rows), rows)
+    assert np.array_equal(plan.first_valid, (S - tb.token_masks.sum(1)).astype(np.int32))
+    assert plan.n_valid_tokens == int(tb.token_masks.sum())
+
+
+def test_plan_pad_seq_and_errors():
+    from neko_b200.policy.packing import build_plan
+    batch = [{"text": [1, 2, 3]}, {"continuous_obs": torch.zeros(2, 3), "continuous_actions": torch.zeros(2, 1)}]
+    plan = build_plan(batch, patch_size=16, context_len=32, pad_seq=True)
+    assert plan.width == 32 and plan.seq_len == 10
+    cfg = O.GatoConfig(context_len=32, pad_seq=True)
+    tb = O.tokenize(batch, cfg)
+    rows = (np.arange(2)[:, None] * 32 + np.arange(31)[None, :])[tb.loss_mask > 0]
+    assert np.array_equal(np.sort(plan.loss_rows), rows)
+    with pytest.raises(AssertionError):
+        build_plan([{"continuous_obs": torch.zeros(3, 2), "continuous_actions": torch.zeros(4, 1)}], patch_size=16, context_len=32, pad_seq=False)
+    with pytest.raises(AssertionError):
+        build_plan([{"images": torch.zeros(1, 3, 20, 32)}], patch_size=16, context_len=32, pad_seq=False)
+    with pytest.raises(AssertionError):
+        build_plan([{}], patch_size=16, context_len=32, pad_seq=False)
+
+
+def test_patch_position_bins_match_oracle():
+    from neko_b200.policy.embeddings import PatchPosEncoding
+    enc = PatchPosEncoding(128, 8).eval()
+    for n_h, n_w in [(6, 6), (14, 14), (2, 3), (5, 1)]:
+        hp, wp = enc.positions(n_h, n_w)
+        assert np.array_equal(hp.numpy(), O.patch_position_indices(n_h))
+        assert np.array_equal(wp.numpy(), O.patch_position_indices(n_w))
+    enc.train()
+    torch.manual_seed(3)
+    hp, wp = enc.positions(4, 3)
+    torch.manual_seed(3)
+    ref_h = O.patch_position_indices(4, 128, True)
+    ref_w = O.patch_position_indices(3, 128, True)
+    assert np.array_equal(hp.numpy(), ref_h) and np.array_equal(wp.numpy(), ref_w)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["NEKO_ROOT"])
+from neko_b200.dp import GradSynchronizer
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+n = 10_000
+arena = torch.arange(n, dtype=torch.float32) * (rank + 1)
+sync = GradSynchronizer(arena, bucket_bytes=4 * 1500)
+# ranges become final back to front of the execution = front to back of the arena
+sync.begin_step()
+for lo, hi in [(0, 4000), (4000, 4064), (4064, 4128), (4128, 9000), (9000, n)]:
+    sync.on_range_ready(lo, hi)
+sync.finish()
+ref = torch.arange(n, dtype=torch.float32) * 1.5
+assert torch.allclose(arena, ref), (arena[:5], ref[:5])
+covered = sorted(sync.launched)
+assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+assert max(hi - lo for lo, hi in covered) <= 1500
+# gradient accumulation: no_sync leaves the arena untouched
+arena2 = torch.ones(100) * (rank + 1)
+s2 = GradSynchronizer(arena2, bucket_bytes=1 << 20)
+with s2.no_sync():
+    s2.on_range_ready(0, 100); s2.finish()
+assert torch.equal(arena2, torch.ones(100) * (rank + 1))
+s2.on_range_ready(0, 100); s2.finish()
+assert torch.allclose(arena2, torch.ones(100) * 1.5)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_grad_synchronizer_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NEKO_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()

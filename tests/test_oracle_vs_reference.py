@@ -1,0 +1,63 @@
+"""Runs the UNMODIFIED reference (when /root/reference is mounted, i.e. in the build container) next to the oracle
+on fresh seeded inputs.  Skipped on the GPU box, where only the committed golden fixtures pin the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gato_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+def _ref_model(cfg, w):
+    ref_shim.set_text_vocab(cfg.text_tokens)
+    G = ref_shim.load_reference_policy_class()
+    m = G(device="cpu", embed_dim=cfg.embed_dim, layers=cfg.layers, heads=cfg.heads, dropout=0.0, resid_mid_channels=128,
+          context_len=cfg.context_len, pad_seq=cfg.pad_seq)
+    m.transformer.drop.p = 0.0
+    m.load_state_dict(w, strict=False)
+    return m.eval()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_forward_backward_bitwise_close(seed):
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=128, text_tokens=200)
+    w = O.make_weights(cfg, seed=seed)
+    rs = np.random.RandomState(seed)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+    batch = [
+        dict(continuous_obs=f32(rs.standard_normal((5, 4)) * 4), continuous_actions=f32(np.clip(rs.standard_normal((5, 2)), -1, 1))),
+        dict(images=f32(rs.randint(0, 256, (2, 3, 32, 32))), discrete_actions=torch.from_numpy(rs.randint(0, 6, (2, 1)).astype(np.int32))),
+        dict(text=rs.randint(0, 200, (23,)).tolist()),
+        dict(images=torch.from_numpy(rs.randint(0, 256, (1, 3, 48, 32)).astype(np.uint8)), text=torch.from_numpy(rs.randint(0, 200, (7,)))),
+    ]
+    m = _ref_model(cfg, w)
+    logits, loss = m(batch, compute_loss=True)
+    loss.backward()
+    for t in w.values():
+        t.requires_grad_(True)
+    out = O.forward(w, batch, cfg, compute_loss=True)
+    out.loss.backward()
+    emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+    assert torch.equal(tok, out.tokens) and torch.equal(tm, out.target_masks) and torch.equal(mk, out.token_masks)
+    assert (emb - out.token_embeddings).abs().max().item() <= 1e-6
+    assert (logits - out.logits).abs().max().item() <= 1e-5
+    assert abs(loss.item() - out.loss.item()) <= 1e-6
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            assert w[n].grad is None or float(w[n].grad.abs().max()) == 0.0
+        else:
+            assert (p.grad - w[n].grad).abs().max().item() <= 1e-5 * max(1.0, float(p.grad.abs().max())), n
+
+
+def test_continuous_tokenizer_random_sweep():
+    ref_shim.install_shims()
+    from gato.policy.input_tokenizers import ContinuousTokenizer
+    cfg = O.GatoConfig()
+    rs = np.random.RandomState(99)
+    x = np.concatenate([rs.standard_normal(300_000) * 10, rs.uniform(-1.5, 1.5, 300_000), np.exp(rs.uniform(-30, 10, 200_000))]).astype(np.float32)
+    for mu_law in (True, False):
+        tok = ContinuousTokenizer(use_mu_law=mu_law, mu=100, M=256, n_bins=1024, offset=50257)
+        ref = tok.encode(torch.from_numpy(x.copy())).numpy()
+        assert np.array_equal(ref, O.discretize(x, mu_law, cfg))
