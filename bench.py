@@ -197,6 +197,7 @@ def run_ours(args):
     tokens_per_step = int(sum(1 for _ in range(0)) or 0)
 
     def step(batch):
+        model.zero_grad()          # what optimizer.zero_grad() does every step in trainer.py:186
         _, loss = model(batch, compute_loss=True)
         loss.backward()
         return loss

@@ -97,10 +97,11 @@ int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, ui
                        uint16_t* y2_bf16 /* nullable second copy */, float* mean, float* rstd, int N, int d,
                        float eps, int out_f16, void* stream);
 /* dx_resid (fp32 [N,d]) += LN'(dy); optional bf16 copy of the updated dx_resid; dgamma/dbeta
- * fp32 [d] are accumulated (caller zeroes them). */
+ * fp32 [d] are accumulated (caller zeroes them).  dx_colsum (nullable, fp32 [d], accumulated): column sums
+ * of the updated dx_resid = the bias gradient of the Conv1D whose output was added into this residual. */
 int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean,
                        const float* rstd, float* dx_resid, uint16_t* dx_bf16, float* dgamma,
-                       float* dbeta, int N, int d, void* stream);
+                       float* dbeta, float* dx_colsum, int N, int d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense GEMM on tcgen05 tensor cores (HF Conv1D addmm trajectory_gpt2.py:222,253,274,277;

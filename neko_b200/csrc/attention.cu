@@ -6,9 +6,11 @@
 // row attends keys in [first_valid[b], query].  Padded query rows (left pad, or the right pad of --pad_seq)
 // are never read by the loss (gato_policy.py:177-180) nor by valid rows; they are written as zeros.
 //
-// Tensor-core path: warp-level mma.sync m16n8k16 bf16 with fp32 accumulation, operands staged in shared
-// memory so that every B fragment is a k-contiguous 32-bit load.  dh = 32 (24 heads x 32 at d=768) makes
-// this op softmax/exp-bound rather than MMA-bound; it is <3% of the step FLOPs.
+// Tensor-core path: warp-level mma.sync m16n8k16 bf16 with fp32 accumulation.  Tiles (64 rows x dh) are
+// brought in with cp.async into a double-buffered shared-memory ring (the next K/V -- or Q/dO -- tile is in
+// flight while the current one is consumed) and fragments come from ldmatrix / ldmatrix.trans, so no
+// transposed copies are ever built.  dh = 32 (24 heads x 32 at d=768) makes this op latency/exp-bound rather
+// than MMA-bound; it is <3% of the step FLOPs.
 #include "common.cuh"
 
 namespace neko {
@@ -22,50 +24,56 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Shared-memory tile of `rows` x `cols` bf16 with an 8-element row pad (keeps 32-bit fragment loads
-// conflict-free: the pitch in words is = 4 mod 8... cols/2 + 4).
-template <int COLS>
+// Shared-memory tile: 64 rows x DH bf16, row pitch DH + 8 elements (16-byte chunks of 8 consecutive rows fall
+// into distinct banks: conflict-free ldmatrix and cp.async).
+template <int DH>
 struct Tile {
-  static constexpr int PITCH = COLS + 8;
-  bf16* p;
-  __device__ __forceinline__ uint32_t ld32(int r, int c) const { return *reinterpret_cast<const uint32_t*>(p + r * PITCH + c); }
-  __device__ __forceinline__ bf16& at(int r, int c) { return p[r * PITCH + c]; }
+  static constexpr int PITCH = DH + 8;
+  static constexpr int BYTES = ATT_BLK * PITCH * 2;
+  uint32_t base;  // shared-space address
+  __device__ __forceinline__ uint32_t addr(int r, int c) const { return base + (uint32_t)(r * PITCH + c) * 2u; }
 };
 
-// A fragment (16 x 16 at column k0) of a row-major smem tile whose rows are the M index.
-template <int COLS>
-__device__ __forceinline__ void load_a_frag(const Tile<COLS>& t, int row0, int k0, int lane, uint32_t (&a)[4]) {
-  const int g = lane >> 2, q = lane & 3;
-  a[0] = t.ld32(row0 + g, k0 + 2 * q);
-  a[1] = t.ld32(row0 + g + 8, k0 + 2 * q);
-  a[2] = t.ld32(row0 + g, k0 + 8 + 2 * q);
-  a[3] = t.ld32(row0 + g + 8, k0 + 8 + 2 * q);
-}
-
-// cooperative loads: rows [r0, r0+64) x DH of one head from the packed qkv / out / dout tensors
+// rows [r0, r0+64) x DH of one head, 16 bytes per cp.async; rows >= r_end are zero-filled
 template <int DH>
-__device__ __forceinline__ void load_tile(Tile<DH> dst, const bf16* __restrict__ src, long long row_pitch, int r0, int r_end) {
-  constexpr int VPR = DH / 8;  // uint4 per row
-  for (int i = threadIdx.x; i < ATT_BLK * VPR; i += ATT_THREADS) {
-    const int r = i / VPR, v = i % VPR;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (r0 + r < r_end) val = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * row_pitch) + v);
-    *reinterpret_cast<uint4*>(dst.p + r * Tile<DH>::PITCH + v * 8) = val;
-  }
-}
-// transposed: dst[c][r] = src[r0 + r][c]
-template <int DH>
-__device__ __forceinline__ void load_tile_t(Tile<ATT_BLK> dst, const bf16* __restrict__ src, long long row_pitch, int r0, int r_end) {
+__device__ __forceinline__ void load_tile_async(const Tile<DH>& dst, const bf16* __restrict__ src, long long row_pitch, int r0, int r_end) {
   constexpr int VPR = DH / 8;
   for (int i = threadIdx.x; i < ATT_BLK * VPR; i += ATT_THREADS) {
-    const int r = i % ATT_BLK, v = i / ATT_BLK;  // consecutive threads -> consecutive rows: conflict-free smem writes
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (r0 + r < r_end) val = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * row_pitch) + v);
-    const bf16* e = reinterpret_cast<const bf16*>(&val);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst.at(v * 8 + j, r) = e[j];
+    const int r = i / VPR, v = i % VPR;
+    const bool ok = (r0 + r) < r_end;
+    const bf16* p = src + (long long)(ok ? (r0 + r) : 0) * row_pitch + v * 8;
+    cp_async16(dst.addr(r, v * 8), p, ok);
   }
+}
+
+// A fragment: rows row0..row0+15, k columns k0..k0+15 of a [row][k] tile
+template <int DH>
+__device__ __forceinline__ void frag_a(const Tile<DH>& t, int row0, int k0, int lane, uint32_t (&a)[4]) {
+  ldsm_x4(t.addr(row0 + (lane & 15), k0 + ((lane >> 4) << 3)), a[0], a[1], a[2], a[3]);
+}
+// B fragments of two adjacent n-tiles (n0..n0+15) for k0..k0+15 from a tile stored [n][k]
+template <int DH>
+__device__ __forceinline__ void frag_b_nk(const Tile<DH>& t, int n0, int k0, int lane, uint32_t (&b)[4]) {
+  ldsm_x4(t.addr(n0 + (lane & 7) + ((lane >> 4) << 3), k0 + (((lane >> 3) & 1) << 3)), b[0], b[1], b[2], b[3]);
+}
+// B fragments of two adjacent n-tiles (n0..n0+15) for k0..k0+15 from a tile stored [k][n]
+template <int DH>
+__device__ __forceinline__ void frag_b_kn(const Tile<DH>& t, int k0, int n0, int lane, uint32_t (&b)[4]) {
+  ldsm_x4_t(t.addr(k0 + (lane & 7) + (((lane >> 3) & 1) << 3), n0 + ((lane >> 4) << 3)), b[0], b[1], b[2], b[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -76,9 +84,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
                                                                bf16* __restrict__ out, bf16* __restrict__ out2, float* __restrict__ lse, int S,
                                                                int S_valid, int H, float scale_log2, int out_f16) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  Tile<DH> sQ{reinterpret_cast<bf16*>(smem_raw)};
-  Tile<DH> sK{sQ.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<ATT_BLK> sVt{sK.p + ATT_BLK * Tile<DH>::PITCH};  // [DH][64 keys]
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const Tile<DH> sQ{s0};
+  auto sK = [&](int bi) { return Tile<DH>{s0 + (1 + bi) * Tile<DH>::BYTES}; };  // double-buffered K / V tiles
+  auto sV = [&](int bi) { return Tile<DH>{s0 + (3 + bi) * Tile<DH>::BYTES}; };
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_BLK;
   const int d = H * DH;
@@ -87,43 +96,64 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   const int lo = first_valid[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
-
   const int q_hi = min(q0 + ATT_BLK, S_valid);  // queries in [max(q0,lo), q_hi) are live
+
   float o[DH / 8][4];
 #pragma unroll
   for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
 
   if (q_hi > lo && q_hi > q0) {
-    load_tile<DH>(sQ, base + h * DH, pitch, q0, S);
-    __syncthreads();
-    uint32_t qa[DH / 16][4];
-#pragma unroll
-    for (int k = 0; k < DH / 16; ++k) load_a_frag<DH>(sQ, warp * 16, k * 16, lane, qa[k]);
-
     const int j_begin = (lo / ATT_BLK) * ATT_BLK;
-    for (int j0 = j_begin; j0 < q_hi; j0 += ATT_BLK) {
+    load_tile_async<DH>(sQ, base + h * DH, pitch, q0, S);
+    load_tile_async<DH>(sK(0), base + d + h * DH, pitch, j_begin, S);
+    load_tile_async<DH>(sV(0), base + 2 * d + h * DH, pitch, j_begin, S);
+    cp_async_commit();
+    uint32_t qa[DH / 16][4];
+    int buf = 0;
+    for (int j0 = j_begin; j0 < q_hi; j0 += ATT_BLK, buf ^= 1) {
+      const bool more = (j0 + ATT_BLK) < q_hi;
+      if (more) {  // prefetch the next K/V tile into the other buffer
+        load_tile_async<DH>(sK(buf ^ 1), base + d + h * DH, pitch, j0 + ATT_BLK, S);
+        load_tile_async<DH>(sV(buf ^ 1), base + 2 * d + h * DH, pitch, j0 + ATT_BLK, S);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
       __syncthreads();
-      load_tile<DH>(sK, base + d + h * DH, pitch, j0, S);
-      load_tile_t<DH>(sVt, base + 2 * d + h * DH, pitch, j0, S);
-      __syncthreads();
+      if (j0 == j_begin) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) frag_a<DH>(sQ, warp * 16, k * 16, lane, qa[k]);
+      }
       float s[ATT_BLK / 8][4];
 #pragma unroll
-      for (int n = 0; n < ATT_BLK / 8; ++n) {
-        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      for (int n2 = 0; n2 < ATT_BLK / 16; ++n2) {
+        s[2 * n2][0] = s[2 * n2][1] = s[2 * n2][2] = s[2 * n2][3] = 0.f;
+        s[2 * n2 + 1][0] = s[2 * n2 + 1][1] = s[2 * n2 + 1][2] = s[2 * n2 + 1][3] = 0.f;
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          mma_bf16(s[n], qa[k], sK.ld32(n * 8 + g, k * 16 + 2 * q), sK.ld32(n * 8 + g, k * 16 + 8 + 2 * q));
+        for (int k = 0; k < DH / 16; ++k) {
+          uint32_t kb[4];
+          frag_b_nk<DH>(sK(buf), n2 * 16, k * 16, lane, kb);
+          mma_bf16(s[2 * n2], qa[k], kb[0], kb[1]);
+          mma_bf16(s[2 * n2 + 1], qa[k], kb[2], kb[3]);
+        }
       }
       // mask + online softmax (rows row_a, row_b; this thread holds keys j0 + n*8 + 2q, +1)
       float mx_a = -INFINITY, mx_b = -INFINITY;
+      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0) || (q0 + ATT_BLK > S_valid);
+      if (need_mask) {
+#pragma unroll
+        for (int n = 0; n < ATT_BLK / 8; ++n) {
+          const int key = j0 + n * 8 + 2 * q;
+          if (key < lo || key > row_a || row_a >= S_valid) s[n][0] = -INFINITY;
+          if (key + 1 < lo || key + 1 > row_a || row_a >= S_valid) s[n][1] = -INFINITY;
+          if (key < lo || key > row_b || row_b >= S_valid) s[n][2] = -INFINITY;
+          if (key + 1 < lo || key + 1 > row_b || row_b >= S_valid) s[n][3] = -INFINITY;
+        }
+      }
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
-        const int key = j0 + n * 8 + 2 * q;
-        if (key < lo || key > row_a || row_a >= S_valid) s[n][0] = -INFINITY;
-        if (key + 1 < lo || key + 1 > row_a || row_a >= S_valid) s[n][1] = -INFINITY;
-        if (key < lo || key > row_b || row_b >= S_valid) s[n][2] = -INFINITY;
-        if (key + 1 < lo || key + 1 > row_b || row_b >= S_valid) s[n][3] = -INFINITY;
         mx_a = fmaxf(mx_a, fmaxf(s[n][0], s[n][1]));
         mx_b = fmaxf(mx_b, fmaxf(s[n][2], s[n][3]));
       }
@@ -139,10 +169,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       float sum_a = 0.f, sum_b = 0.f;
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
-        s[n][0] = exp2f(s[n][0] * scale_log2 - ref_a);
-        s[n][1] = exp2f(s[n][1] * scale_log2 - ref_a);
-        s[n][2] = exp2f(s[n][2] * scale_log2 - ref_b);
-        s[n][3] = exp2f(s[n][3] * scale_log2 - ref_b);
+        s[n][0] = exp2f(fmaf(s[n][0], scale_log2, -ref_a));
+        s[n][1] = exp2f(fmaf(s[n][1], scale_log2, -ref_a));
+        s[n][2] = exp2f(fmaf(s[n][2], scale_log2, -ref_b));
+        s[n][3] = exp2f(fmaf(s[n][3], scale_log2, -ref_b));
         sum_a += s[n][0] + s[n][1];
         sum_b += s[n][2] + s[n][3];
       }
@@ -152,7 +182,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       for (int n = 0; n < DH / 8; ++n) {
         o[n][0] *= corr_a; o[n][1] *= corr_a; o[n][2] *= corr_b; o[n][3] *= corr_b;
       }
-      // O += P V  (P from the score accumulators, V^T tile gives k-contiguous B fragments)
+      // O += P V  (P from the score accumulators; V tile is [key][dh] -> transposed ldmatrix)
 #pragma unroll
       for (int kk = 0; kk < ATT_BLK / 16; ++kk) {
         uint32_t pa[4];
@@ -161,9 +191,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
         pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
         pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-        for (int n = 0; n < DH / 8; ++n)
-          mma_bf16(o[n], pa, sVt.ld32(n * 8 + g, kk * 16 + 2 * q), sVt.ld32(n * 8 + g, kk * 16 + 8 + 2 * q));
+        for (int n2 = 0; n2 < DH / 16; ++n2) {
+          uint32_t vb[4];
+          frag_b_kn<DH>(sV(buf), kk * 16, n2 * 16, lane, vb);
+          mma_bf16(o[2 * n2], pa, vb[0], vb[1]);
+          mma_bf16(o[2 * n2 + 1], pa, vb[2], vb[3]);
+        }
       }
+      __syncthreads();  // everyone is done with this buffer before the prefetch two iterations ahead reuses it
     }
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
@@ -194,30 +229,156 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward
+// backward.  dQ kernel first (it also produces delta[b,h,i] = sum_c dO[i,c] O[i,c] from the tiles it holds),
+// then the dK/dV kernel.  No atomics: each kernel owns its output rows and recomputes P.
 // ---------------------------------------------------------------------------------------------
-// delta[b,h,i] = sum_c dO[i,c] * O[i,c]
-__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                                         int B, int S, int H, int dh, int out_f16) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)B * S * H;
-  if (w >= total) return;
-  const int h = (int)(w % H);
-  const long long bs = w / H;  // b*S + s
-  const bf16* o = out + bs * (long long)H * dh + (long long)h * dh;
-  const bf16* g = dout + bs * (long long)H * dh + (long long)h * dh;
-  float acc = 0.f;
-  for (int c = lane * 2; c < dh; c += 64) {
-    const uint32_t ou = *reinterpret_cast<const uint32_t*>(o + c);
-    const float2 a = out_f16 ? unpack_f16x2(ou) : unpack_bf16x2(ou);
-    const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + c));
-    acc += a.x * bb.x + a.y * bb.y;
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                                                                  const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                                  float* __restrict__ delta, const int32_t* __restrict__ first_valid,
+                                                                  bf16* __restrict__ dqkv, int S, int S_valid, int H, float scale,
+                                                                  float scale_log2, int out_f16) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const Tile<DH> sQ{s0};
+  const Tile<DH> sdO{s0 + Tile<DH>::BYTES};
+  const Tile<DH> sO{s0 + 2 * Tile<DH>::BYTES};
+  auto sK = [&](int bi) { return Tile<DH>{s0 + (3 + bi) * Tile<DH>::BYTES}; };
+  auto sV = [&](int bi) { return Tile<DH>{s0 + (5 + bi) * Tile<DH>::BYTES}; };
+  float* s_delta = reinterpret_cast<float*>(smem_raw + 7 * Tile<DH>::BYTES);
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_BLK;
+  const int d = H * DH;
+  const long long pitch = 3LL * d;
+  const bf16* base = qkv + (long long)b * S * pitch;
+  const bf16* dob = dout + (long long)b * S * d + h * DH;
+  const bf16* ob = out + (long long)b * S * d + h * DH;
+  const int lo = first_valid[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
+  const int q_hi = min(q0 + ATT_BLK, S_valid);
+  const float kLog2e = 1.4426950408889634f;
+  float* delta_b = delta + ((long long)b * H + h) * S;
+
+  float dq[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+
+  const bool live = (q_hi > lo) && (q_hi > q0);
+  if (!live) {
+    // delta of dead rows is never read with a non-zero P, but keep the buffer defined
+    if (threadIdx.x < ATT_BLK && q0 + threadIdx.x < S) delta_b[q0 + threadIdx.x] = 0.f;
+  } else {
+    const float* lse_b = lse + ((long long)b * H + h) * S;
+    const int j_begin = (lo / ATT_BLK) * ATT_BLK;
+    load_tile_async<DH>(sQ, base + h * DH, pitch, q0, S);
+    load_tile_async<DH>(sdO, dob, d, q0, S);
+    load_tile_async<DH>(sO, ob, d, q0, S);
+    load_tile_async<DH>(sK(0), base + d + h * DH, pitch, j_begin, S);
+    load_tile_async<DH>(sV(0), base + 2 * d + h * DH, pitch, j_begin, S);
+    cp_async_commit();
+    const float lse_a = (row_a < S) ? lse_b[row_a] * kLog2e : INFINITY, lse_bb = (row_b < S) ? lse_b[row_b] * kLog2e : INFINITY;
+    uint32_t qa[DH / 16][4], doa[DH / 16][4];
+    float del_a = 0.f, del_b = 0.f;
+    int buf = 0;
+    for (int j0 = j_begin; j0 < q_hi; j0 += ATT_BLK, buf ^= 1) {
+      const bool more = (j0 + ATT_BLK) < q_hi;
+      if (more) {
+        load_tile_async<DH>(sK(buf ^ 1), base + d + h * DH, pitch, j0 + ATT_BLK, S);
+        load_tile_async<DH>(sV(buf ^ 1), base + 2 * d + h * DH, pitch, j0 + ATT_BLK, S);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (j0 == j_begin) {
+        // delta = rowsum(dO * O): two threads per row, then published through shared memory
+        {
+          const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+          const bf16* po = reinterpret_cast<const bf16*>(smem_raw + 2 * Tile<DH>::BYTES) + r * Tile<DH>::PITCH + half * (DH / 2);
+          const bf16* pg = reinterpret_cast<const bf16*>(smem_raw + 1 * Tile<DH>::BYTES) + r * Tile<DH>::PITCH + half * (DH / 2);
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < DH / 2; c += 2) {
+            const uint32_t ou = *reinterpret_cast<const uint32_t*>(po + c);
+            const float2 a = out_f16 ? unpack_f16x2(ou) : unpack_bf16x2(ou);
+            const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pg + c));
+            acc += a.x * bb.x + a.y * bb.y;
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (half == 0) {
+            s_delta[r] = acc;
+            if (q0 + r < S) delta_b[q0 + r] = acc;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          frag_a<DH>(sQ, warp * 16, k * 16, lane, qa[k]);
+          frag_a<DH>(sdO, warp * 16, k * 16, lane, doa[k]);
+        }
+        __syncthreads();
+        del_a = s_delta[warp * 16 + g];
+        del_b = s_delta[warp * 16 + g + 8];
+      }
+      float s[ATT_BLK / 8][4], dp[ATT_BLK / 8][4];
+#pragma unroll
+      for (int n2 = 0; n2 < ATT_BLK / 16; ++n2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f; dp[2 * n2][e] = dp[2 * n2 + 1][e] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          uint32_t kb[4], vb[4];
+          frag_b_nk<DH>(sK(buf), n2 * 16, k * 16, lane, kb);
+          frag_b_nk<DH>(sV(buf), n2 * 16, k * 16, lane, vb);
+          mma_bf16(s[2 * n2], qa[k], kb[0], kb[1]);
+          mma_bf16(s[2 * n2 + 1], qa[k], kb[2], kb[3]);
+          mma_bf16(dp[2 * n2], doa[k], vb[0], vb[1]);
+          mma_bf16(dp[2 * n2 + 1], doa[k], vb[2], vb[3]);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < ATT_BLK / 8; ++n) {
+        const int key = j0 + n * 8 + 2 * q;
+        const bool va = row_a < S_valid, vb = row_b < S_valid;
+        const float p0 = (va && key >= lo && key <= row_a) ? exp2f(fmaf(s[n][0], scale_log2, -lse_a)) : 0.f;
+        const float p1 = (va && key + 1 >= lo && key + 1 <= row_a) ? exp2f(fmaf(s[n][1], scale_log2, -lse_a)) : 0.f;
+        const float p2 = (vb && key >= lo && key <= row_b) ? exp2f(fmaf(s[n][2], scale_log2, -lse_bb)) : 0.f;
+        const float p3 = (vb && key + 1 >= lo && key + 1 <= row_b) ? exp2f(fmaf(s[n][3], scale_log2, -lse_bb)) : 0.f;
+        s[n][0] = p0 * (dp[n][0] - del_a) * scale;
+        s[n][1] = p1 * (dp[n][1] - del_a) * scale;
+        s[n][2] = p2 * (dp[n][2] - del_b) * scale;
+        s[n][3] = p3 * (dp[n][3] - del_b) * scale;
+      }
+      // dQ += dS K   (K tile is [key][dh]: k index = key -> transposed ldmatrix)
+#pragma unroll
+      for (int kk = 0; kk < ATT_BLK / 16; ++kk) {
+        uint32_t sa[4];
+        sa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        sa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        sa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        sa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int n2 = 0; n2 < DH / 16; ++n2) {
+          uint32_t kb[4];
+          frag_b_kn<DH>(sK(buf), kk * 16, n2 * 16, lane, kb);
+          mma_bf16(dq[2 * n2], sa, kb[0], kb[1]);
+          mma_bf16(dq[2 * n2 + 1], sa, kb[2], kb[3]);
+        }
+      }
+      __syncthreads();
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const int b = (int)(bs / S), s = (int)(bs % S);
-    delta[((long long)b * H + h) * S + s] = acc;
+  bf16* dqb = dqkv + (long long)b * S * pitch + h * DH;
+  if (row_a < S) {
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n)
+      *reinterpret_cast<uint32_t*>(dqb + (long long)row_a * pitch + n * 8 + 2 * q) = pack_bf16x2(dq[n][0], dq[n][1]);
+  }
+  if (row_b < S) {
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n)
+      *reinterpret_cast<uint32_t*>(dqb + (long long)row_b * pitch + n * 8 + 2 * q) = pack_bf16x2(dq[n][2], dq[n][3]);
   }
 }
 
@@ -228,14 +389,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
                                                                    const int32_t* __restrict__ first_valid, bf16* __restrict__ dqkv,
                                                                    int S, int S_valid, int H, float scale, float scale_log2) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  Tile<DH> sK{reinterpret_cast<bf16*>(smem_raw)};
-  Tile<DH> sV{sK.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<DH> sQ{sV.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<DH> sdO{sQ.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<ATT_BLK> sQt{sdO.p + ATT_BLK * Tile<DH>::PITCH};            // [DH][64 queries]
-  Tile<ATT_BLK> sdOt{sQt.p + DH * Tile<ATT_BLK>::PITCH};           // [DH][64 queries]
-  float* s_lse = reinterpret_cast<float*>(sdOt.p + DH * Tile<ATT_BLK>::PITCH);
-  float* s_delta = s_lse + ATT_BLK;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const Tile<DH> sK{s0};
+  const Tile<DH> sV{s0 + Tile<DH>::BYTES};
+  auto sQ = [&](int bi) { return Tile<DH>{s0 + (2 + bi) * Tile<DH>::BYTES}; };
+  auto sdO = [&](int bi) { return Tile<DH>{s0 + (4 + bi) * Tile<DH>::BYTES}; };
+  float* s_lse = reinterpret_cast<float*>(smem_raw + 6 * Tile<DH>::BYTES);  // [2][64]
+  float* s_delta = s_lse + 2 * ATT_BLK;                                      // [2][64]
 
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * ATT_BLK;
   const int d = H * DH;
@@ -247,6 +407,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   const int lo = first_valid[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int key_a = j0 + warp * 16 + g, key_b = key_a + 8;
+  const float kLog2e = 1.4426950408889634f;
 
   float dk[DH / 8][4], dv[DH / 8][4];
 #pragma unroll
@@ -256,61 +417,79 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   }
   const bool live = (j0 + ATT_BLK > lo) && (j0 < S_valid);
   if (live) {
-    load_tile<DH>(sK, base + d + h * DH, pitch, j0, S);
-    load_tile<DH>(sV, base + 2 * d + h * DH, pitch, j0, S);
-    for (int i0 = j0; i0 < S_valid; i0 += ATT_BLK) {
-      __syncthreads();
-      load_tile<DH>(sQ, base + h * DH, pitch, i0, S);
-      load_tile<DH>(sdO, dob, d, i0, S);
-      load_tile_t<DH>(sQt, base + h * DH, pitch, i0, S);
-      load_tile_t<DH>(sdOt, dob, d, i0, S);
+    auto load_q_tile = [&](int bufi, int i0) {
+      load_tile_async<DH>(sQ(bufi), base + h * DH, pitch, i0, S);
+      load_tile_async<DH>(sdO(bufi), dob, d, i0, S);
       if (threadIdx.x < ATT_BLK) {
         const int i = i0 + threadIdx.x;
-        s_lse[threadIdx.x] = (i < S) ? lse_b[i] : INFINITY;
-        s_delta[threadIdx.x] = (i < S) ? delta_b[i] : 0.f;
+        s_lse[bufi * ATT_BLK + threadIdx.x] = (i < S) ? lse_b[i] * kLog2e : INFINITY;
+        s_delta[bufi * ATT_BLK + threadIdx.x] = (i < S) ? delta_b[i] : 0.f;
+      }
+    };
+    load_tile_async<DH>(sK, base + d + h * DH, pitch, j0, S);
+    load_tile_async<DH>(sV, base + 2 * d + h * DH, pitch, j0, S);
+    load_q_tile(0, j0);
+    cp_async_commit();
+    uint32_t ka[DH / 16][4], va[DH / 16][4];
+    int buf = 0;
+    for (int i0 = j0; i0 < S_valid; i0 += ATT_BLK, buf ^= 1) {
+      const bool more = (i0 + ATT_BLK) < S_valid;
+      if (more) {
+        load_q_tile(buf ^ 1, i0 + ATT_BLK);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
+      if (i0 == j0) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          frag_a<DH>(sK, warp * 16, k * 16, lane, ka[k]);
+          frag_a<DH>(sV, warp * 16, k * 16, lane, va[k]);
+        }
+      }
       // S^T = K Q^T and dP^T = V dO^T   (rows = this warp's 16 keys, cols = 64 queries)
       float st[ATT_BLK / 8][4], dpt[ATT_BLK / 8][4];
 #pragma unroll
-      for (int n = 0; n < ATT_BLK / 8; ++n) {
-        st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
-        dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
-      }
+      for (int n2 = 0; n2 < ATT_BLK / 16; ++n2) {
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k) {
-        uint32_t ka[4], va[4];
-        load_a_frag<DH>(sK, warp * 16, k * 16, lane, ka);
-        load_a_frag<DH>(sV, warp * 16, k * 16, lane, va);
+        for (int e = 0; e < 4; ++e) { st[2 * n2][e] = st[2 * n2 + 1][e] = 0.f; dpt[2 * n2][e] = dpt[2 * n2 + 1][e] = 0.f; }
 #pragma unroll
-        for (int n = 0; n < ATT_BLK / 8; ++n) {
-          mma_bf16(st[n], ka, sQ.ld32(n * 8 + g, k * 16 + 2 * q), sQ.ld32(n * 8 + g, k * 16 + 8 + 2 * q));
-          mma_bf16(dpt[n], va, sdO.ld32(n * 8 + g, k * 16 + 2 * q), sdO.ld32(n * 8 + g, k * 16 + 8 + 2 * q));
+        for (int k = 0; k < DH / 16; ++k) {
+          uint32_t qb[4], gb[4];
+          frag_b_nk<DH>(sQ(buf), n2 * 16, k * 16, lane, qb);
+          frag_b_nk<DH>(sdO(buf), n2 * 16, k * 16, lane, gb);
+          mma_bf16(st[2 * n2], ka[k], qb[0], qb[1]);
+          mma_bf16(st[2 * n2 + 1], ka[k], qb[2], qb[3]);
+          mma_bf16(dpt[2 * n2], va[k], gb[0], gb[1]);
+          mma_bf16(dpt[2 * n2 + 1], va[k], gb[2], gb[3]);
         }
       }
       // P^T = exp(S^T * scale - lse[query]); dS^T = P^T * (dP^T - delta[query]) * scale
+      const float* lsp = s_lse + buf * ATT_BLK;
+      const float* dlp = s_delta + buf * ATT_BLK;
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
         const int c0 = n * 8 + 2 * q;  // local query column
         const int qi0 = i0 + c0, qi1 = qi0 + 1;
-        const float l0 = s_lse[c0], l1 = s_lse[c0 + 1];
-        const float kLog2e = 1.4426950408889634f;
+        const float l0 = lsp[c0], l1 = lsp[c0 + 1];
         const bool ok00 = (key_a >= lo) && (key_a <= qi0) && (qi0 < S_valid);
         const bool ok01 = (key_a >= lo) && (key_a <= qi1) && (qi1 < S_valid);
         const bool ok10 = (key_b >= lo) && (key_b <= qi0) && (qi0 < S_valid);
         const bool ok11 = (key_b >= lo) && (key_b <= qi1) && (qi1 < S_valid);
-        const float p00 = ok00 ? exp2f(st[n][0] * scale_log2 - l0 * kLog2e) : 0.f;
-        const float p01 = ok01 ? exp2f(st[n][1] * scale_log2 - l1 * kLog2e) : 0.f;
-        const float p10 = ok10 ? exp2f(st[n][2] * scale_log2 - l0 * kLog2e) : 0.f;
-        const float p11 = ok11 ? exp2f(st[n][3] * scale_log2 - l1 * kLog2e) : 0.f;
-        const float d0 = s_delta[c0], d1 = s_delta[c0 + 1];
+        const float p00 = ok00 ? exp2f(fmaf(st[n][0], scale_log2, -l0)) : 0.f;
+        const float p01 = ok01 ? exp2f(fmaf(st[n][1], scale_log2, -l1)) : 0.f;
+        const float p10 = ok10 ? exp2f(fmaf(st[n][2], scale_log2, -l0)) : 0.f;
+        const float p11 = ok11 ? exp2f(fmaf(st[n][3], scale_log2, -l1)) : 0.f;
+        const float d0 = dlp[c0], d1 = dlp[c0 + 1];
         dpt[n][0] = p00 * (dpt[n][0] - d0) * scale;
         dpt[n][1] = p01 * (dpt[n][1] - d1) * scale;
         dpt[n][2] = p10 * (dpt[n][2] - d0) * scale;
         dpt[n][3] = p11 * (dpt[n][3] - d1) * scale;
         st[n][0] = p00; st[n][1] = p01; st[n][2] = p10; st[n][3] = p11;
       }
-      // dV += P^T dO ; dK += dS^T Q   (k index = query: B fragments from the transposed tiles)
+      // dV += P^T dO ; dK += dS^T Q   (k index = query: tiles are [query][dh] -> transposed ldmatrix)
 #pragma unroll
       for (int kk = 0; kk < ATT_BLK / 16; ++kk) {
         uint32_t pa[4], sa[4];
@@ -323,11 +502,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         sa[2] = pack_bf16x2(dpt[2 * kk + 1][0], dpt[2 * kk + 1][1]);
         sa[3] = pack_bf16x2(dpt[2 * kk + 1][2], dpt[2 * kk + 1][3]);
 #pragma unroll
-        for (int n = 0; n < DH / 8; ++n) {
-          mma_bf16(dv[n], pa, sdOt.ld32(n * 8 + g, kk * 16 + 2 * q), sdOt.ld32(n * 8 + g, kk * 16 + 8 + 2 * q));
-          mma_bf16(dk[n], sa, sQt.ld32(n * 8 + g, kk * 16 + 2 * q), sQt.ld32(n * 8 + g, kk * 16 + 8 + 2 * q));
+        for (int n2 = 0; n2 < DH / 16; ++n2) {
+          uint32_t gb[4], qb[4];
+          frag_b_kn<DH>(sdO(buf), kk * 16, n2 * 16, lane, gb);
+          frag_b_kn<DH>(sQ(buf), kk * 16, n2 * 16, lane, qb);
+          mma_bf16(dv[2 * n2], pa, gb[0], gb[1]);
+          mma_bf16(dv[2 * n2 + 1], pa, gb[2], gb[3]);
+          mma_bf16(dk[2 * n2], sa, qb[0], qb[1]);
+          mma_bf16(dk[2 * n2 + 1], sa, qb[2], qb[3]);
         }
       }
+      __syncthreads();
     }
   }
   bf16* dkb = dqkv + (long long)b * S * pitch + d + h * DH;
@@ -348,111 +533,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   }
 }
 
-// dQ: one CTA owns 64 queries of one head and sweeps the key tiles at or above... below the diagonal.
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                                  const float* __restrict__ lse, const float* __restrict__ delta,
-                                                                  const int32_t* __restrict__ first_valid, bf16* __restrict__ dqkv,
-                                                                  int S, int S_valid, int H, float scale, float scale_log2) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Tile<DH> sQ{reinterpret_cast<bf16*>(smem_raw)};
-  Tile<DH> sdO{sQ.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<DH> sK{sdO.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<DH> sV{sK.p + ATT_BLK * Tile<DH>::PITCH};
-  Tile<ATT_BLK> sKt{sV.p + ATT_BLK * Tile<DH>::PITCH};  // [DH][64 keys]
-
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_BLK;
-  const int d = H * DH;
-  const long long pitch = 3LL * d;
-  const bf16* base = qkv + (long long)b * S * pitch;
-  const bf16* dob = dout + (long long)b * S * d + h * DH;
-  const int lo = first_valid[b];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
-  const int q_hi = min(q0 + ATT_BLK, S_valid);
-  const float kLog2e = 1.4426950408889634f;
-
-  float dq[DH / 8][4];
-#pragma unroll
-  for (int n = 0; n < DH / 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
-
-  if (q_hi > lo && q_hi > q0) {
-    const float* lse_b = lse + ((long long)b * H + h) * S;
-    const float* delta_b = delta + ((long long)b * H + h) * S;
-    const float lse_a = (row_a < S) ? lse_b[row_a] * kLog2e : INFINITY, lse_bb = (row_b < S) ? lse_b[row_b] * kLog2e : INFINITY;
-    const float del_a = (row_a < S) ? delta_b[row_a] : 0.f, del_b = (row_b < S) ? delta_b[row_b] : 0.f;
-    load_tile<DH>(sQ, base + h * DH, pitch, q0, S);
-    load_tile<DH>(sdO, dob, d, q0, S);
-    __syncthreads();
-    uint32_t qa[DH / 16][4], doa[DH / 16][4];
-#pragma unroll
-    for (int k = 0; k < DH / 16; ++k) {
-      load_a_frag<DH>(sQ, warp * 16, k * 16, lane, qa[k]);
-      load_a_frag<DH>(sdO, warp * 16, k * 16, lane, doa[k]);
-    }
-    const int j_begin = (lo / ATT_BLK) * ATT_BLK;
-    for (int j0 = j_begin; j0 < q_hi; j0 += ATT_BLK) {
-      __syncthreads();
-      load_tile<DH>(sK, base + d + h * DH, pitch, j0, S);
-      load_tile<DH>(sV, base + 2 * d + h * DH, pitch, j0, S);
-      load_tile_t<DH>(sKt, base + d + h * DH, pitch, j0, S);
-      __syncthreads();
-      float s[ATT_BLK / 8][4], dp[ATT_BLK / 8][4];
-#pragma unroll
-      for (int n = 0; n < ATT_BLK / 8; ++n) {
-        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          mma_bf16(s[n], qa[k], sK.ld32(n * 8 + g, k * 16 + 2 * q), sK.ld32(n * 8 + g, k * 16 + 8 + 2 * q));
-          mma_bf16(dp[n], doa[k], sV.ld32(n * 8 + g, k * 16 + 2 * q), sV.ld32(n * 8 + g, k * 16 + 8 + 2 * q));
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < ATT_BLK / 8; ++n) {
-        const int key = j0 + n * 8 + 2 * q;
-        const bool va = row_a < S_valid, vb = row_b < S_valid;
-        const float p0 = (va && key >= lo && key <= row_a) ? exp2f(s[n][0] * scale_log2 - lse_a) : 0.f;
-        const float p1 = (va && key + 1 >= lo && key + 1 <= row_a) ? exp2f(s[n][1] * scale_log2 - lse_a) : 0.f;
-        const float p2 = (vb && key >= lo && key <= row_b) ? exp2f(s[n][2] * scale_log2 - lse_bb) : 0.f;
-        const float p3 = (vb && key + 1 >= lo && key + 1 <= row_b) ? exp2f(s[n][3] * scale_log2 - lse_bb) : 0.f;
-        s[n][0] = p0 * (dp[n][0] - del_a) * scale;
-        s[n][1] = p1 * (dp[n][1] - del_a) * scale;
-        s[n][2] = p2 * (dp[n][2] - del_b) * scale;
-        s[n][3] = p3 * (dp[n][3] - del_b) * scale;
-      }
-#pragma unroll
-      for (int kk = 0; kk < ATT_BLK / 16; ++kk) {
-        uint32_t sa[4];
-        sa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-        sa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-        sa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        sa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-        for (int n = 0; n < DH / 8; ++n)
-          mma_bf16(dq[n], sa, sKt.ld32(n * 8 + g, kk * 16 + 2 * q), sKt.ld32(n * 8 + g, kk * 16 + 8 + 2 * q));
-      }
-    }
-  }
-  bf16* dqb = dqkv + (long long)b * S * pitch + h * DH;
-  if (row_a < S) {
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n)
-      *reinterpret_cast<uint32_t*>(dqb + (long long)row_a * pitch + n * 8 + 2 * q) = pack_bf16x2(dq[n][0], dq[n][1]);
-  }
-  if (row_b < S) {
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n)
-      *reinterpret_cast<uint32_t*>(dqb + (long long)row_b * pitch + n * 8 + 2 * q) = pack_bf16x2(dq[n][2], dq[n][3]);
-  }
-}
-
+static size_t fwd_smem() { return 5 * (size_t)Tile<DH>::BYTES; }
 template <int DH>
-static size_t fwd_smem() { return (size_t)(2 * ATT_BLK * Tile<DH>::PITCH + DH * Tile<ATT_BLK>::PITCH) * sizeof(bf16); }
+static size_t dq_smem() { return 7 * (size_t)Tile<DH>::BYTES + ATT_BLK * sizeof(float); }
 template <int DH>
-static size_t dkv_smem() { return (size_t)(4 * ATT_BLK * Tile<DH>::PITCH + 2 * DH * Tile<ATT_BLK>::PITCH) * sizeof(bf16) + 2 * ATT_BLK * sizeof(float); }
-template <int DH>
-static size_t dq_smem() { return (size_t)(4 * ATT_BLK * Tile<DH>::PITCH + DH * Tile<ATT_BLK>::PITCH) * sizeof(bf16); }
+static size_t dkv_smem() { return 6 * (size_t)Tile<DH>::BYTES + 4 * ATT_BLK * sizeof(float); }
 
 template <int DH>
 static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int out_f16, cudaStream_t st) {
@@ -467,20 +553,20 @@ static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2,
 }
 
 template <int DH>
-static int launch_bwd(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, const int32_t* fv, bf16* dqkv, int B,
-                      int S, int S_valid, int H, cudaStream_t st) {
-  const size_t s1 = dkv_smem<DH>(), s2 = dq_smem<DH>();
-  cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_bwd_dkv)");
-  e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, const int32_t* fv, bf16* dqkv,
+                      int B, int S, int S_valid, int H, int out_f16, cudaStream_t st) {
+  const size_t s1 = dq_smem<DH>(), s2 = dkv_smem<DH>();
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_bwd_dq)");
+  e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_bwd_dkv)");
   const float scale = 1.0f / sqrtf((float)DH);
   const float scale_log2 = 1.4426950408889634f * scale;
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_bwd_dkv_kernel<DH><<<grid, ATT_THREADS, s1, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2);
-  NEKO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
-  attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, s2, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2);
+  attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, s1, st>>>(qkv, out, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, out_f16);
   NEKO_LAUNCH_CHECK("attn_bwd_dq_kernel");
+  attn_bwd_dkv_kernel<DH><<<grid, ATT_THREADS, s2, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2);
+  NEKO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return NEKO_OK;
 }
 
@@ -512,19 +598,18 @@ int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t*
   using namespace neko;
   NEKO_REQUIRE(qkv && out && dout && lse && first_valid && dqkv && delta, "attention_bwd: null pointer");
   NEKO_REQUIRE(B > 0 && S > 0 && H > 0 && S_valid > 0 && S_valid <= S, "attention_bwd: bad sizes");
+  NEKO_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dout) & 15) == 0, "attention_bwd: misaligned");
   cudaStream_t st = as_stream(stream);
   const bf16* x = reinterpret_cast<const bf16*>(qkv);
   const bf16* o = reinterpret_cast<const bf16*>(out);
   const bf16* g = reinterpret_cast<const bf16*>(dout);
   bf16* dx = reinterpret_cast<bf16*>(dqkv);
-  const long long warps = (long long)B * S * H;
-  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(o, g, delta, B, S, H, dh, out_f16);
-  NEKO_LAUNCH_CHECK("attn_delta_kernel");
   switch (dh) {
-    case 16: return launch_bwd<16>(x, g, lse, delta, first_valid, dx, B, S, S_valid, H, st);
-    case 32: return launch_bwd<32>(x, g, lse, delta, first_valid, dx, B, S, S_valid, H, st);
-    case 64: return launch_bwd<64>(x, g, lse, delta, first_valid, dx, B, S, S_valid, H, st);
-    case 128: return launch_bwd<128>(x, g, lse, delta, first_valid, dx, B, S, S_valid, H, st);
+    case 16: return launch_bwd<16>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
+    case 32: return launch_bwd<32>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
+    case 64: return launch_bwd<64>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
+    case 128: return launch_bwd<128>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
     default: set_error("attention: head dim %d not supported (16, 32, 64, 128)", dh); return NEKO_EINVAL;
   }
 }

@@ -62,81 +62,95 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-// Each CTA owns `rows_per_cta` consecutive rows; warps stride over them.  The row lives in registers (x and dy
-// only: xhat and gamma*dy are recomputed in the second pass to keep the register count, hence the occupancy of
-// this pure streaming kernel, reasonable).  dgamma / dbeta partials go to shared-memory accumulators (RED.shared),
-// then one global atomicAdd per column per CTA.
-template <int LN_MAX_VEC>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+// Backward.  Threads own COLUMNS (one float4 = 4 columns each, blockDim = d/4 rounded up to a warp), a CTA walks
+// its rows four at a time: 12 independent 128/64-bit loads per thread are in flight before the first use, the
+// 8 row statistics are block-reduced with shuffles + one __syncthreads, and the column sums dgamma / dbeta / colsum
+// live in 12 registers per thread for the whole kernel (one global atomicAdd per column per CTA at the end).
+constexpr int LNB_ROWS = 4;
+
+__global__ void __launch_bounds__(512) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ dx_resid,
                                                             bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int N, int d, int rows_per_cta) {
-  extern __shared__ float smem[];  // [2][d] accumulators
-  const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  const int nv = d >> 2;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) smem[i] = 0.f;
-  __syncthreads();
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+                                                            float* __restrict__ dbeta, float* __restrict__ dx_colsum, int N, int d,
+                                                            int rows_per_cta) {
+  __shared__ float red[2][16][2 * LNB_ROWS];  // [parity][warp][s1 x4, s2 x4]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int c4 = threadIdx.x;            // this thread's float4 column group
+  const bool act = c4 < (d >> 2);
+  const float4 g = act ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(N, row0 + rows_per_cta);
-  for (int row = row0 + wid; row < row1; row += nwarps) {
-    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    const uint2* dy2 = reinterpret_cast<const uint2*>(dy + (size_t)row * d);
-    const float mu = mean[row], rs = rstd[row];
-    float4 xv[LN_MAX_VEC];
-    uint2 dv[LN_MAX_VEC];
-    float s1 = 0.f, s2 = 0.f;
+  const float inv_d = 1.0f / (float)d;
+  int parity = 0;
+  for (int rb = row0; rb < row1; rb += LNB_ROWS, parity ^= 1) {
+    float4 xv[LNB_ROWS], rv[LNB_ROWS];
+    uint2 dv[LNB_ROWS];
+    float mu[LNB_ROWS], rs[LNB_ROWS];
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; ++k) {
-      const int i = lane + k * 32;
-      if (i < nv) {
-        xv[k] = x4[i];
-        dv[k] = dy2[i];
-      }
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      const int row = rb + r;
+      const bool ok = act && row < row1;
+      const size_t off = (size_t)(ok ? row : row0) * d;
+      xv[r] = ok ? reinterpret_cast<const float4*>(x + off)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[r] = ok ? reinterpret_cast<const uint2*>(dy + off)[c4] : make_uint2(0u, 0u);
+      rv[r] = ok ? reinterpret_cast<const float4*>(dx_resid + off)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      mu[r] = (row < row1) ? __ldg(mean + row) : 0.f;
+      rs[r] = (row < row1) ? __ldg(rstd + row) : 0.f;
+    }
+    float s[2 * LNB_ROWS];
+    float4 gy[LNB_ROWS], xh[LNB_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      const float2 d01 = unpack_bf16x2(dv[r].x), d23 = unpack_bf16x2(dv[r].y);
+      xh[r] = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);
+      gy[r] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
+      s[r] = (gy[r].x + gy[r].y) + (gy[r].z + gy[r].w);
+      s[LNB_ROWS + r] = (gy[r].x * xh[r].x + gy[r].y * xh[r].y) + (gy[r].z * xh[r].z + gy[r].w * xh[r].w);
+      // column sums of dy and dy * xhat
+      ab.x += d01.x; ab.y += d01.y; ab.z += d23.x; ab.w += d23.y;
+      ag.x += d01.x * xh[r].x; ag.y += d01.y * xh[r].y; ag.z += d23.x * xh[r].z; ag.w += d23.y * xh[r].w;
     }
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; ++k) {
-      const int i = lane + k * 32;
-      if (i < nv) {
-        const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
-        const float4 g = __ldg(g4 + i);
-        const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
-        s1 += (g0 + g1) + (g2 + g3);
-        s2 += (g0 * (xv[k].x - mu) + g1 * (xv[k].y - mu)) + (g2 * (xv[k].z - mu) + g3 * (xv[k].w - mu));
-      }
-    }
-    s1 = warp_sum(s1) / (float)d;
-    s2 = warp_sum(s2) * rs / (float)d;
-    float4* r4 = reinterpret_cast<float4*>(dx_resid + (size_t)row * d);
-    uint2* o2 = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * d) : nullptr;
+    for (int i = 0; i < 2 * LNB_ROWS; ++i) s[i] = warp_sum(s[i]);
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; ++k) {
-      const int i = lane + k * 32;
-      if (i < nv) {
-        const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
-        const float4 g = __ldg(g4 + i);
-        const float h0 = (xv[k].x - mu) * rs, h1 = (xv[k].y - mu) * rs, h2 = (xv[k].z - mu) * rs, h3 = (xv[k].w - mu) * rs;
-        float4 r = r4[i];
-        r.x += rs * (d01.x * g.x - s1 - h0 * s2);
-        r.y += rs * (d01.y * g.y - s1 - h1 * s2);
-        r.z += rs * (d23.x * g.z - s1 - h2 * s2);
-        r.w += rs * (d23.y * g.w - s1 - h3 * s2);
-        r4[i] = r;
-        if (o2) o2[i] = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
-        float* sg = smem + 4 * i;
-        float* sb = smem + d + 4 * i;
-        atomicAdd(sg + 0, d01.x * h0); atomicAdd(sg + 1, d01.y * h1); atomicAdd(sg + 2, d23.x * h2); atomicAdd(sg + 3, d23.y * h3);
-        atomicAdd(sb + 0, d01.x); atomicAdd(sb + 1, d01.y); atomicAdd(sb + 2, d23.x); atomicAdd(sb + 3, d23.y);
+      for (int i = 0; i < 2 * LNB_ROWS; ++i) red[parity][wid][i] = s[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2 * LNB_ROWS; ++i) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[parity][w][i];
+      s[i] = t * inv_d;
+    }
+#pragma unroll
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      const int row = rb + r;
+      if (act && row < row1) {
+        const float m1 = s[r], m2 = s[LNB_ROWS + r];
+        float4 o = rv[r];
+        o.x += rs[r] * (gy[r].x - m1 - xh[r].x * m2);
+        o.y += rs[r] * (gy[r].y - m1 - xh[r].y * m2);
+        o.z += rs[r] * (gy[r].z - m1 - xh[r].z * m2);
+        o.w += rs[r] * (gy[r].w - m1 - xh[r].w * m2);
+        const size_t off = (size_t)row * d;
+        reinterpret_cast<float4*>(dx_resid + off)[c4] = o;
+        if (dx_bf16) reinterpret_cast<uint2*>(dx_bf16 + off)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
       }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(dgamma + i, smem[i]);
-    atomicAdd(dbeta + i, smem[d + i]);
+  if (act) {
+    float* pg = dgamma + 4 * c4;
+    float* pb = dbeta + 4 * c4;
+    atomicAdd(pg, ag.x); atomicAdd(pg + 1, ag.y); atomicAdd(pg + 2, ag.z); atomicAdd(pg + 3, ag.w);
+    atomicAdd(pb, ab.x); atomicAdd(pb + 1, ab.y); atomicAdd(pb + 2, ab.z); atomicAdd(pb + 3, ab.w);
+    if (dx_colsum) {
+      float* pc = dx_colsum + 4 * c4;
+      atomicAdd(pc, ac.x); atomicAdd(pc + 1, ac.y); atomicAdd(pc + 2, ac.z); atomicAdd(pc + 3, ac.w);
+    }
   }
 }
 
@@ -161,23 +175,18 @@ int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, ui
 }
 
 int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean, const float* rstd,
-                       float* dx_resid, uint16_t* dx_bf16, float* dgamma, float* dbeta, int N, int d, void* stream) {
+                       float* dx_resid, uint16_t* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int N, int d, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(dy_bf16 && x && gamma && mean && rstd && dx_resid && dgamma && dbeta, "layernorm_bwd: null pointer");
   NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_bwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
-  const int threads = 256;
-  // one resident wave (2 CTAs per SM at ~100 registers), each CTA a contiguous row range: few CTAs keep the
-  // final global atomics (2*d per CTA, all on the same 2*d addresses) cheap
+  const int threads = ((d / 4 + 31) / 32) * 32;  // one float4 column group per thread
+  // ~2 CTAs per SM: enough loads in flight (12 per thread), few enough CTAs that the final atomics stay cheap
   int ctas = sm_count() * 2;
   int rows_per_cta = (N + ctas - 1) / ctas;
-  if (rows_per_cta < 8) rows_per_cta = 8;
+  rows_per_cta = ((rows_per_cta + LNB_ROWS - 1) / LNB_ROWS) * LNB_ROWS;
   ctas = (N + rows_per_cta - 1) / rows_per_cta;
-  const size_t smem = 2 * (size_t)d * sizeof(float);
-#define NEKO_LN_BWD(NV) layernorm_bwd_kernel<NV><<<ctas, threads, smem, as_stream(stream)>>>(reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid, reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, N, d, rows_per_cta)
-  const int need = (d / 4 + 31) / 32;
-  if (need <= 1) NEKO_LN_BWD(1); else if (need <= 2) NEKO_LN_BWD(2); else if (need <= 4) NEKO_LN_BWD(4);
-  else if (need <= 6) NEKO_LN_BWD(6); else if (need <= 8) NEKO_LN_BWD(8); else NEKO_LN_BWD(16);
-#undef NEKO_LN_BWD
+  layernorm_bwd_kernel<<<ctas, threads, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid,
+                                                                reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dx_colsum, N, d, rows_per_cta);
   NEKO_LAUNCH_CHECK("layernorm_bwd_kernel");
   return NEKO_OK;
 }

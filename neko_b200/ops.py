@@ -96,10 +96,11 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf16=None):
+def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf16=None, dx_colsum=None):
     N, d = x.shape
     check(load().neko_layernorm_bwd(_p(dy_bf16), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx_bf16),
-                                    _p(dgamma), _p(dbeta), C.c_int(N), C.c_int(d), stream_ptr()), "neko_layernorm_bwd")
+                                    _p(dgamma), _p(dbeta), _p(dx_colsum), C.c_int(N), C.c_int(d), stream_ptr()),
+          "neko_layernorm_bwd")
 
 
 # ------------------------------------------------------------------------------------------

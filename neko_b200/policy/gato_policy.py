@@ -135,6 +135,7 @@ class _FusedStep(torch.autograd.Function):
         ctx.policy = policy
         ctx.state = state
         ctx.n_params = len(params)
+        ctx.set_materialize_grads(False)  # never let autograd zero-fill a [B,S,V] gradient for the logits output
         ctx.mark_non_differentiable(logits)
         if loss is None:
             loss = torch.zeros((), device=logits.device)
@@ -143,6 +144,8 @@ class _FusedStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _g_logits, g_loss):
+        if g_loss is None:
+            return (None, None) + (None,) * ctx.n_params
         ctx.policy._engine_backward(ctx.state, g_loss)
         # gradients were written straight into the flat arena behind every parameter's .grad
         return (None, None) + (None,) * ctx.n_params
@@ -266,12 +269,13 @@ class GatoPolicy(nn.Module):
         names = ["predict_token.weight", "transformer.ln_f.weight", "transformer.ln_f.bias"]
         for i in reversed(range(self.layers)):
             p = f"transformer.h.{i}."
-            names += [p + "mlp.c_proj.weight", p + "mlp.c_proj.bias"]
+            # the four weight matrices first (fully overwritten by their wgrad GEMM), then the small vectors
+            # (accumulated with atomics: they need zeroing, and are contiguous so one memset per layer does it)
+            names += [p + "mlp.c_proj.weight", p + "mlp.c_fc.weight", p + "attn.c_proj.weight", p + "attn.c_attn.weight"]
             if self.transformer.config.gate:
                 names += [p + "mlp.gated_layer.weight", p + "mlp.gated_layer.bias"]
-            names += [p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "ln_2.weight", p + "ln_2.bias",
-                      p + "attn.c_proj.weight", p + "attn.c_proj.bias", p + "attn.c_attn.weight", p + "attn.c_attn.bias",
-                      p + "ln_1.weight", p + "ln_1.bias"]
+            names += [p + "mlp.c_proj.bias", p + "mlp.c_fc.bias", p + "ln_2.weight", p + "ln_2.bias",
+                      p + "attn.c_proj.bias", p + "attn.c_attn.bias", p + "ln_1.weight", p + "ln_1.bias"]
         names += [n for n, _ in self.named_parameters() if n.startswith("image_embedding.")]
         names += ["pos_embed_observation.weight", "separator_token", "embed_token.weight", "transformer.wte.weight"]
         return names
@@ -304,6 +308,22 @@ class GatoPolicy(nn.Module):
         self._offs = offs
         self._order = order
         self._params = params
+        # gradient ranges that must start from zero each step (everything except the matrices a single non-split
+        # or self-zeroing wgrad GEMM overwrites)
+        overwritten = {"predict_token.weight"} | {f"transformer.h.{i}.{m}.weight" for i in range(self.layers)
+                                                  for m in ("mlp.c_proj", "mlp.c_fc", "attn.c_proj", "attn.c_attn")}
+        ranges, cur = [], None
+        for k, n in enumerate(order):
+            end = offs[order[k + 1]] if k + 1 < len(order) else total
+            if n in overwritten:
+                if cur is not None:
+                    ranges.append(tuple(cur))
+                    cur = None
+            else:
+                cur = [offs[n], end] if cur is None else [cur[0], end]
+        if cur is not None:
+            ranges.append(tuple(cur))
+        self._zero_ranges = ranges
         self._bf16_versions = None
         self._grad_live = False
 
@@ -360,7 +380,8 @@ class GatoPolicy(nn.Module):
                 if g is None or g.data_ptr() != self._grad_arena.data_ptr() + 4 * self._offs[n]:
                     live = False
         if not live:
-            self._grad_arena.zero_()
+            for lo, hi in self._zero_ranges:
+                self._grad_arena[lo:hi].zero_()
             for n, p in self._params.items():
                 p.grad = None
         for n, p in self._params.items():
@@ -759,7 +780,11 @@ class GatoPolicy(nn.Module):
         dx.zero_()
         dxb = self._buf("dx_bf16", (N, d), torch.bfloat16)
         lnf = self.transformer.ln_f
-        ops.layernorm_bwd(dhf, st.x_last, lnf.weight, st.mf, st.rf, dx, G("transformer.ln_f.weight"), G("transformer.ln_f.bias"), dxb)
+        last = f"transformer.h.{self.layers - 1}."
+        # the bias gradient of a residual-feeding Conv1D is the column sum of the residual gradient: LN backward
+        # emits it for free (mlp.c_proj.bias of the block below, attn.c_proj.bias of the same block)
+        ops.layernorm_bwd(dhf, st.x_last, lnf.weight, st.mf, st.rf, dx, G("transformer.ln_f.weight"), G("transformer.ln_f.bias"), dxb,
+                          dx_colsum=G(last + "mlp.c_proj.bias"))
         self.launches += 2
         self._notify("transformer.ln_f.weight", "transformer.ln_f.bias")
 
@@ -771,7 +796,6 @@ class GatoPolicy(nn.Module):
             # MLP: x2 = x1 + gelu(ln2 @ Wfc + b) @ Wproj + b
             ops.gemm(fact, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_proj.weight"), accumulate=acc,
                      M=4 * d, N=d, K=N)
-            ops.colsum(dxb, G(pre + "mlp.c_proj.bias"), accumulate=True)
             dpre = self._buf("dfpre", (N, 4 * d), torch.bfloat16)
             ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre)
             ops.gemm(ln2, dpre, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_fc.weight"), accumulate=acc,
@@ -779,11 +803,11 @@ class GatoPolicy(nn.Module):
             ops.colsum(dpre, G(pre + "mlp.c_fc.bias"), accumulate=True)
             dln = self._buf("dln", (N, d), torch.bfloat16)
             ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_BF16, out=dln)
-            ops.layernorm_bwd(dln, x1, blk.ln_2.weight, m2, r2, dx, G(pre + "ln_2.weight"), G(pre + "ln_2.bias"), dxb)
+            ops.layernorm_bwd(dln, x1, blk.ln_2.weight, m2, r2, dx, G(pre + "ln_2.weight"), G(pre + "ln_2.bias"), dxb,
+                              dx_colsum=G(pre + "attn.c_proj.bias"))
             # attention: x1 = x0 + attn(ln1 @ Wqkv + b) @ Wproj + b
             ops.gemm(att, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "attn.c_proj.weight"), accumulate=acc,
                      M=d, N=d, K=N)
-            ops.colsum(dxb, G(pre + "attn.c_proj.bias"), accumulate=True)
             datt = self._buf("datt", (N, d), torch.bfloat16)
             ops.gemm(dxb, Wb(pre + "attn.c_proj.weight"), epilogue=ops.EPI_BF16, out=datt)
             dqkv = self._buf("dqkv", (N, 3 * d), torch.bfloat16)
@@ -794,8 +818,9 @@ class GatoPolicy(nn.Module):
                      M=d, N=3 * d, K=N)
             ops.colsum(dqkv, G(pre + "attn.c_attn.bias"), accumulate=True)
             ops.gemm(dqkv, Wb(pre + "attn.c_attn.weight"), epilogue=ops.EPI_BF16, out=dln)
-            ops.layernorm_bwd(dln, x0, blk.ln_1.weight, m1, r1, dx, G(pre + "ln_1.weight"), G(pre + "ln_1.bias"), dxb)
-            self.launches += 17
+            ops.layernorm_bwd(dln, x0, blk.ln_1.weight, m1, r1, dx, G(pre + "ln_1.weight"), G(pre + "ln_1.bias"), dxb,
+                              dx_colsum=G(f"transformer.h.{i - 1}.mlp.c_proj.bias") if i > 0 else None)
+            self.launches += 14
             self._notify(pre + "mlp.c_proj.weight", pre + "ln_1.bias")
 
         # ---- embeddings ---------------------------------------------------------------------------------------

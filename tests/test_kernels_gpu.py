@@ -192,8 +192,10 @@ def test_layernorm(ops, N, d):
     dg = torch.zeros(d, device="cuda")
     db = torch.zeros(d, device="cuda")
     dx_bf = torch.empty(N, d, device="cuda", dtype=torch.bfloat16)
-    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, dx_bf)
+    cs = torch.zeros(d, device="cuda")
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, dx_bf, dx_colsum=cs)
     assert (dx - (resid + xr.grad)).abs().max().item() < 2e-4
+    assert (cs - dx.sum(0)).abs().max().item() < 1e-3 * math.sqrt(N) + 1e-3
     assert (dx_bf.float() - dx).abs().max().item() < 0.05
     assert (dg - gr.grad).abs().max().item() < 2e-3 * math.sqrt(N)
     assert (db - br.grad).abs().max().item() < 2e-3 * math.sqrt(N)

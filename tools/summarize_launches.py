@@ -13,9 +13,9 @@ for r in csv.DictReader(lines):
     val = float(r["Metric Value"].replace(",", ""))
     unit = r.get("Metric Unit", "ns")
     ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(unit, 1)
-    rows.append((r["Kernel Name"], ns))
+    rows.append((r["Kernel Name"], ns, r.get("Grid Size", "")))
 # keep the launches of the last step
-starts = [i for i, (k, _) in enumerate(rows) if "tokenize_embed" in k]
+starts = [i for i, r in enumerate(rows) if "tokenize_embed" in r[0]]
 if len(starts) >= 2:
     # the cast of the weights precedes tokenize; include it
     s = starts[-1]
@@ -23,7 +23,7 @@ if len(starts) >= 2:
         s -= 1
     rows = rows[s:]
 agg = OrderedDict()
-for k, ns in rows:
+for k, ns, _g in rows:
     name = k.split("(")[0]
     c, t = agg.get(name, (0, 0.0))
     agg[name] = (c + 1, t + ns)
@@ -32,3 +32,8 @@ print(f"launches in one step: {len(rows)}   summed device time: {total / 1e6:.3f
 print(f"{'kernel':60s} {'count':>6s} {'ms':>9s} {'share':>7s}")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{name[:60]:60s} {c:6d} {t / 1e6:9.3f} {100 * t / total:6.1f}%")
+
+print()
+print("launch sequence of the step (kernel, grid, us):")
+for k, ns, g in rows:
+    print(f"  {k.split('(')[0].replace('void ', '').replace('neko::', '')[:46]:46s} {g:>18s} {ns / 1e3:9.1f}")
