@@ -55,6 +55,7 @@ struct GemmParams {
   int flags;       // NEKO_GEMM_*_F16
   int splits;      // split-K factor (fp32 reduction into C when > 1)
   int n_fast;      // tile rasterisation: consecutive work units walk N first (else M first)
+  int pair;        // 1: cta_group::2 CTA pairs (256 x BN tile per pair)
   int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
   int kb_per_split;
 };
@@ -98,6 +99,43 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ---- cluster / CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {  // shared::cta address -> shared::cluster address of CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -419,6 +457,11 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+// PAIR = true: the two CTAs of a cluster (one TPC) form a cta_group::2 pair that computes one 256 x BN tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues M=256 MMAs that read both
+// shared memories and write both tensor memories, so every operand byte crosses L2 -> SM once per PAIR instead of
+// once per CTA (the single-CTA kernel is bound by that traffic, profiles/r01_ncu_gemm_full.md).
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
@@ -428,8 +471,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = p.BN;
   const int stages = p.stages;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // position inside the CTA pair
+  const int BNL = PAIR ? BN / 2 : BN;                    // rows of the B tile staged by THIS CTA
   const uint32_t a_bytes = BM * BK * 2;
-  const uint32_t b_bytes = (uint32_t)BN * BK * 2;
+  const uint32_t b_bytes = (uint32_t)BNL * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* staging = smem + (size_t)stages * stage_bytes;  // 1024-byte aligned: stage_bytes is a multiple of 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
@@ -449,59 +494,83 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), PAIR ? 2 : 1);   // pair: one expect_tx arrival per CTA, both on the leader's barrier
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
+      mbar_init(tempty_bar(a), PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // pair: both CTAs' epilogues release the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  const int m_blocks = (p.M + BM - 1) / BM;
+  constexpr int TM = PAIR ? 2 * BM : BM;  // rows of C per work unit
+  const int m_blocks = (p.M + TM - 1) / TM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
   const long long tiles = (long long)m_blocks * n_blocks;
   const long long units = tiles * p.splits;  // work unit = (tile, k-split)
+  const long long u_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;   // both CTAs of a pair walk the same units
+  const long long u_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      for (long long u = u_first; u < units; u += u_step) {
         const long long t = u / p.splits;
         const int ks = (int)(u - t * p.splits);
-        const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * BM;
-        const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
+        const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * TM + (int)rank * BM;   // this CTA's 128 rows
+        const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN + (int)rank * BNL;  // this CTA's slice of B
         const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          mbar_expect_tx(full_bar(stage), stage_bytes);
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+          if (PAIR) {
+            // both CTAs post their bytes on the LEADER's full barrier; the loads land in the local shared memory
+            const uint32_t fb = mapa_shared(full_bar(stage), 0);
+            mbar_expect_tx_cluster(fb, stage_bytes);
+            if (!p.a_mn) {
+              tma_load_2d_pair(sa, &map_a, fb, k0, m0);
+            } else {
+              for (int g = 0; g < BM / 64; ++g) tma_load_2d_pair(sa + g * (BK * 128), &map_a, fb, m0 + g * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_pair(sb, &map_b, fb, k0, n0);
+            } else {
+              for (int g = 0; g < BNL / 64; ++g) tma_load_2d_pair(sb + g * (BK * 128), &map_b, fb, n0 + g * 64, k0);
+            }
           } else {
-            for (int g = 0; g < BM / 64; ++g)                  // boxes {64 m, 64 k}
-              tma_load_2d(sa + g * (BK * 128), &map_a, full_bar(stage), m0 + g * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);  // box {64 k, BN n}
-          } else {
-            for (int g = 0; g < BN / 64; ++g)
-              tma_load_2d(sb + g * (BK * 128), &map_b, full_bar(stage), n0 + g * 64, k0);
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+            } else {
+              for (int g = 0; g < BM / 64; ++g)                  // boxes {64 m, 64 k}
+                tma_load_2d(sa + g * (BK * 128), &map_a, full_bar(stage), m0 + g * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);  // box {64 k, BN n}
+            } else {
+              for (int g = 0; g < BN / 64; ++g)
+                tma_load_2d(sb + g * (BK * 128), &map_b, full_bar(stage), n0 + g * 64, k0);
+            }
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
@@ -509,16 +578,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: fp32 accumulate, {f16|bf16} x {f16|bf16}, M=128, N=BN, operand majors
+    if (lane == 0 && rank == 0) {  // pair: only the leader CTA issues
+      // instruction descriptor: fp32 accumulate, {f16|bf16} x {f16|bf16}, M=128 (256 per pair), N=BN, operand majors
       const uint32_t a_fmt = (p.flags & NEKO_GEMM_A_F16) ? 0u : 1u, b_fmt = (p.flags & NEKO_GEMM_B_F16) ? 0u : 1u;  // F16 = 0, BF16 = 1
       const uint32_t idesc = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      for (long long u = u_first; u < units; u += u_step) {
         const int ks = (int)(u % p.splits);
         const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
@@ -535,12 +604,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // MN-major: step 16 k-rows = two 8-row swizzle atoms = 2048 bytes.
             const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 2048, BK * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else      tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // ring slot free once these MMAs have read it
+          if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));  // ring slot free (in both CTAs)
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));      // accumulator complete
+        if (PAIR) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));      // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -556,10 +626,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     stg.wide = (p.epi == NEKO_EPI_F32 || p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16) ? 1 : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (long long u = u_first; u < units; u += u_step) {
       const long long t = u / p.splits;
       const bool split_first = (u - t * p.splits) == 0;
-      const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * BM;
+      const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * TM + (int)rank * BM;
       const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -576,17 +646,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();  // staging buffers must outlive their bulk reads
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: the peer may still read this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -693,27 +766,37 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.epi = epilogue; p.accumulate = accumulate; p.flags = flags;
   p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.C3 = C3; p.ldc3 = ldc3; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
-  // tile width and split-K factor: minimise  waves x (main loop + epilogue)  in units of one 128-wide k-block.
-  // The narrow tile pays ~15% more operand traffic per flop; the epilogue of a tile costs about 3 k-blocks per
-  // 128 columns.  Split-K (fp32 RED into C) is only used for plain fp32 outputs: the weight gradients, whose M x N
-  // is a handful of tiles while K is the whole token axis.
+  // tile shape, CTA pairing and split-K factor: minimise  waves x (main loop + epilogue)  in units of one k-block of a
+  // 128 x 128 tile.  Per-k-block costs reflect the measured operand-traffic bound (profiles/): a single CTA moves
+  // 32 KB (BN=128) or 48 KB (BN=256) per k-block, a CTA of a pair 24 KB / 32 KB for the same MMA work.  Split-K
+  // (fp32 reduce-add into C) is only used for plain fp32 outputs: the weight gradients, whose M x N is a handful
+  // of tiles while K is the whole token axis.
   const int sms = sm_count();
-  const long long mb_ = (M + BM - 1) / BM;
   const int kblocks = (K + BK - 1) / BK;
   const bool can_split = (epilogue == NEKO_EPI_F32) && (bias == nullptr);
+  // CTA pairs pay off where the main loop dominates (measured per shape, profiles/r01_gemm_shapes.md): plain fp32
+  // outputs (LM head, weight gradients) and wide 16-bit outputs; narrow-N and epilogue-heavy launches stay single-CTA.
+  int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (epilogue == NEKO_EPI_BF16 && N >= 2048)) ? 1 : 0;
+  if (const char* force = getenv("NEKO_GEMM_PAIR")) { pair_lo = pair_hi = atoi(force) ? 1 : 0; }
   double best = 1e30;
-  p.BN = 128; p.splits = 1;
-  for (int bn = 128; bn <= 256; bn += 128) {
-    if (bn == 256 && N <= 128) break;
-    const long long tiles_ = mb_ * ((N + bn - 1) / bn);
-    for (int sp = 1; sp <= (can_split ? 16 : 1); ++sp) {
-      if (sp > 1 && kblocks / sp < 8) break;
-      const long long units_ = tiles_ * sp;
-      const double per_unit = ((kblocks + sp - 1) / sp) * (bn == 128 ? 1.15 : 2.0) + 3.0 * (bn / 128) * (sp > 1 ? 1.5 : 1.0);
-      const double cost = (double)((units_ + sms - 1) / sms) * per_unit;
-      if (cost < best - 1e-9) { best = cost; p.BN = bn; p.splits = sp; }
+  p.BN = 128; p.splits = 1; p.pair = 0;
+  for (int pr = pair_lo; pr <= pair_hi; ++pr) {
+    const long long mb_ = (M + (pr ? 2 * BM : BM) - 1) / (pr ? 2 * BM : BM);
+    const int workers = pr ? sms / 2 : sms;
+    for (int bn = 128; bn <= 256; bn += 128) {
+      if (bn == 256 && N <= 128) break;
+      const double kb_cost = pr ? (bn == 128 ? 0.95 : 1.5) : (bn == 128 ? 1.15 : 2.0);
+      const long long tiles_ = mb_ * ((N + bn - 1) / bn);
+      for (int sp = 1; sp <= (can_split ? 16 : 1); ++sp) {
+        if (sp > 1 && kblocks / sp < 8) break;
+        const long long units_ = tiles_ * sp;
+        const double per_unit = ((kblocks + sp - 1) / sp) * kb_cost + 3.0 * (bn / 128) * (sp > 1 ? 1.5 : 1.0);
+        const double cost = (double)((units_ + workers - 1) / workers) * per_unit;
+        if (cost < best - 1e-9) { best = cost; p.BN = bn; p.splits = sp; p.pair = pr; }
+      }
     }
   }
+  const long long mb_ = (M + (p.pair ? 2 * BM : BM) - 1) / (p.pair ? 2 * BM : BM);
   if (const char* force = getenv("NEKO_GEMM_BN")) { const int v = atoi(force); if (v == 128 || v == 256) p.BN = v; }
   if (const char* force = getenv("NEKO_GEMM_SPLITS")) { const int v = atoi(force); if (v >= 1 && can_split) p.splits = v; }
   // rasterisation: the operand that is re-read across the concurrently running tiles should be the small one --
@@ -728,7 +811,8 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, as_stream(stream));
     if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(gemm split-K)");
   }
-  const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  const int bnl = p.pair ? p.BN / 2 : p.BN;  // B rows staged per CTA
+  const int stage_bytes = BM * BK * 2 + bnl * BK * 2;
   p.stages = (SMEM_BUDGET - 1024 - 256 - STAGING_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   const bool out_bf16 = (epilogue == NEKO_EPI_BF16 || epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_DGELU_BF16);
@@ -764,20 +848,39 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
   else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
-  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)p.BN, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
+  if (!p.b_mn) rc = make_map(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, BK, (unsigned)bnl, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
   else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
 
   const size_t smem = (size_t)p.stages * stage_bytes + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm pair)");
     attr_set = true;
   }
-  const long long units = (long long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN) * p.splits;
-  const int grid = (int)(units < sms ? units : sms);
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, mc, mc2, mc3, p);
+  const long long units = mb_ * ((N + p.BN - 1) / p.BN) * p.splits;
+  if (p.pair) {
+    const int pairs = sms / 2;
+    const int grid = 2 * (int)(units < pairs ? units : pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, mc, mc2, mc3, p);
+    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm pair)");
+  } else {
+    const int grid = (int)(units < sms ? units : sms);
+    gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, mc, mc2, mc3, p);
+  }
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return NEKO_OK;
 }
