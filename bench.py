@@ -186,6 +186,7 @@ def run_ours(args):
     model.transformer.drop.p = 0.0
     model.head_mode = args.head
     model.materialize_logits = not args.lean
+    model.use_cuda_graphs = not args.no_graphs
     model.train()
     sync = None
     if world > 1:
@@ -211,6 +212,28 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(dev_batch)
     torch.cuda.synchronize()
+    if args.graph_probe:
+        # experiment: how much of the step is launch gaps?  capture one whole fwd+bwd into a CUDA graph and replay it
+        gph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(dev_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gph):
+            step(dev_batch)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            gph.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            gph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        print(f"graph probe: {g0.elapsed_time(g1) / args.steps:.4f} ms/step replayed", file=sys.stderr)
 
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
     clk = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False)
@@ -221,8 +244,6 @@ def run_ours(args):
                                    stdout=clk, stderr=subprocess.DEVNULL)
         except OSError:
             smi = None
-    gemm_log = []
-    ops.GEMM_TIMING = gemm_log
     l0 = model.launches
     if world > 1:
         dist.barrier()
@@ -235,11 +256,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ops.GEMM_TIMING = None
     ms = e0.elapsed_time(e1)
     launches = model.launches - l0
-    gemm_ms = sum(g[0].elapsed_time(g[1]) for g in gemm_log)
-    gemm_fl = sum(g[2] for g in gemm_log)
+
+    # ---- roofline of the dominant kernel: CUDA events around every tensor-core GEMM launch.  The timed region above
+    # replays the step from CUDA graphs (no room for per-launch events), so the same step is run eagerly right after it
+    # with the events in place; kernels, shapes and order are identical.
+    gemm_log = []
+    graphs_on = model.use_cuda_graphs
+    model.use_cuda_graphs = False
+    for _ in range(2):
+        step(dev_batch)
+    torch.cuda.synchronize()
+    ops.GEMM_TIMING = gemm_log
+    inst_steps = min(args.steps, 5)
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(inst_steps):
+        step(dev_batch)
+    i1.record()
+    torch.cuda.synchronize()
+    ops.GEMM_TIMING = None
+    model.use_cuda_graphs = graphs_on
+    eager_ms = i0.elapsed_time(i1) / inst_steps
+    gemm_ms = sum(g[0].elapsed_time(g[1]) for g in gemm_log) / inst_steps * args.steps   # scaled to the timed step count
+    gemm_fl = sum(g[2] for g in gemm_log) / inst_steps * args.steps
     if args.gemm_report and rank == 0:
         agg = {}
         for g in gemm_log:
@@ -248,7 +289,7 @@ def run_ours(args):
         print("GEMM report (M, N, K, a_mn, b_mn, epilogue): launches/step, avg us, TFLOP/s", file=sys.stderr)
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             us = t / c * 1e3
-            print(f"  {str(k):44s} {c // args.steps:3d} {us:9.1f} {2.0 * k[0] * k[1] * k[2] / us / 1e6:8.1f}  total/step {t / args.steps:7.3f} ms", file=sys.stderr)
+            print(f"  {str(k):44s} {c // inst_steps:3d} {us:9.1f} {2.0 * k[0] * k[1] * k[2] / us / 1e6:8.1f}  total/step {t / inst_steps:7.3f} ms", file=sys.stderr)
 
     # ---- timed region 2: end to end from pinned host tensors ---------------------------------------------
     for _ in range(2):
@@ -290,7 +331,7 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[args.config], "name": args.config, "tokens_per_step_per_gpu": tokens_per_step,
                    "padded_positions": N, "loss_rows": n_rows, "head": ("loss-rows only (lean)" if args.lean else f"dense logits, {args.head} backward"),
                    "l2_policy": "per-step activations (>1.6 GB logits alone) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"dp{world}", "model_tflop_per_step_dense": round(model_flops_per_step(cfgd, N, S) / 1e12, 3)},
+                   "parallelism": f"dp{world}", "cuda_graphs": bool(model.use_cuda_graphs), "model_tflop_per_step_dense": round(model_flops_per_step(cfgd, N, S) / 1e12, 3)},
         "clocks": parse_clocks(clk.name),
         "e2e": {"value": round(e2e_tps, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(batch_bytes(host_batch) + 4096),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / args.steps, 4)},
@@ -298,7 +339,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(achieved / peak_tf, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "gemm_ms_per_step": round(gemm_ms / args.steps, 4), "gemm_share_of_step": round(gemm_ms / ms, 4),
+                     "gemm_ms_per_step": round(gemm_ms / args.steps, 4), "gemm_share_of_step": round(gemm_ms / args.steps / eager_ms, 4),
+                     "timing": "CUDA events around each GEMM launch in an eager pass of the same step run right after the timed region "
+                               f"(eager step {eager_ms:.3f} ms; the timed region replays CUDA graphs)",
                      "model_flops_frac": round(model_flops_per_step(cfgd, N, S) * args.steps / (ms / 1e3) / 1e12 / peak_tf, 4)},
     }
     try:
@@ -326,6 +369,8 @@ def main():
     ap.add_argument("--head", default="dense", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
     ap.add_argument("--lean", action="store_true", help="evaluate the LM head on loss rows only (forward returns no logits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step from CUDA graphs")
+    ap.add_argument("--graph-probe", action="store_true", help="experiment: replay the step from a CUDA graph")
     ap.add_argument("--gemm-report", action="store_true", help="per-shape GEMM timings (CUDA events) on stderr")
     args = ap.parse_args()
     if args.impl == "reference":

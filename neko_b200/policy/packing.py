@@ -197,17 +197,26 @@ class Stager:
     """One pinned host buffer + one device buffer per batch: every small input (descriptors, scalars, ids,
     loss rows) crosses PCIe in a single cudaMemcpyAsync."""
 
+    RING = 3  # pinned staging buffers in rotation: the host may run this many steps ahead of the copy engine
+
     def __init__(self, device: torch.device):
         self.device = device
+        self._ring = []          # [(pinned buffer, event recorded after its last H2D copy)]
+        self._next = 0
         self._pinned: Optional[torch.Tensor] = None
         self._dev: Optional[torch.Tensor] = None
 
     def _ensure(self, nbytes: int):
-        if self._pinned is None or self._pinned.numel() < nbytes:
+        if self._dev is None or self._dev.numel() < nbytes:
             cap = max(nbytes, 1 << 20)
             cap = 1 << (cap - 1).bit_length()
-            self._pinned = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            torch.cuda.synchronize(self.device)
+            self._ring = [(torch.empty(cap, dtype=torch.uint8, pin_memory=True), torch.cuda.Event()) for _ in range(self.RING)]
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        # the asynchronous copy out of a pinned buffer must have run before the host overwrites it again
+        self._pinned, self._event = self._ring[self._next]
+        self._next = (self._next + 1) % self.RING
+        self._event.synchronize()
 
     def upload(self, plan: BatchPlan):
         """Returns device views: descs(u8), fvals(f32), ivals(i32), first_valid(i32), loss_rows(i32) and the
@@ -216,12 +225,20 @@ class Stager:
             return (n + 255) // 256 * 256
         host_f = all(not t.is_cuda for t in plan.fvals)
         host_i = all(not t.is_cuda for t in plan.ivals)
-        sizes = [plan.descs.nbytes, plan.n_f * 4 if host_f else 0, plan.n_i * 4 if host_i else 0,
-                 plan.first_valid.nbytes, plan.loss_rows.nbytes]
+        # every region always exists in the (pointer-stable) device buffer, whatever the source of the values: CUDA
+        # graphs captured on this batch shape keep reading the same addresses
+        sizes = [plan.descs.nbytes, plan.n_f * 4, plan.n_i * 4, plan.first_valid.nbytes, plan.loss_rows.nbytes]
         offs = np.cumsum([0] + [al(s) for s in sizes])
         total = int(offs[-1])
         self._ensure(total)
         pin = self._pinned
+        dev = self._dev
+
+        def view(i, dtype):
+            return dev[offs[i]:offs[i] + sizes[i]].view(dtype)
+
+        h2d = 0
+        # descriptors + first_valid + loss rows (+ host-resident values): one pinned -> device copy each contiguous run
         pin[offs[0]:offs[0] + sizes[0]] = torch.from_numpy(plan.descs)
         if host_f and plan.n_f:
             torch.cat(plan.fvals, out=pin[offs[1]:offs[1] + sizes[1]].view(torch.float32))
@@ -230,19 +247,21 @@ class Stager:
         pin[offs[3]:offs[3] + sizes[3]] = torch.from_numpy(plan.first_valid.view(np.uint8))
         if sizes[4]:
             pin[offs[4]:offs[4] + sizes[4]] = torch.from_numpy(plan.loss_rows.view(np.uint8))
-        dev = self._dev
-        dev[:total].copy_(pin[:total], non_blocking=True)
-        h2d = total
-
-        def view(i, dtype):
-            return dev[offs[i]:offs[i] + sizes[i]].view(dtype)
-        descs = dev[offs[0]:offs[0] + sizes[0]]
-        if host_f:
-            fv = view(1, torch.float32)
-        else:  # inputs already live on the device (the reference's ControlTask does this): gather there
-            fv = torch.cat([t.to(self.device) for t in plan.fvals]) if plan.n_f else dev[:0].view(torch.float32)
-        if host_i:
-            iv = view(2, torch.int32)
+        if host_f and host_i:
+            dev[:total].copy_(pin[:total], non_blocking=True)
+            h2d = total
         else:
-            iv = torch.cat([t.to(self.device) for t in plan.ivals]) if plan.n_i else dev[:0].view(torch.int32)
+            for i in range(5):
+                if sizes[i] and not ((i == 1 and not host_f) or (i == 2 and not host_i)):
+                    dev[offs[i]:offs[i] + sizes[i]].copy_(pin[offs[i]:offs[i] + sizes[i]], non_blocking=True)
+                    h2d += sizes[i]
+            # inputs already on the device (the reference's ControlTask puts them there): gather device-to-device
+            if not host_f and plan.n_f:
+                torch.cat([t.to(self.device) for t in plan.fvals], out=view(1, torch.float32))
+            if not host_i and plan.n_i:
+                torch.cat([t.to(self.device) for t in plan.ivals], out=view(2, torch.int32))
+        self._event.record(torch.cuda.current_stream(self.device))
+        descs = dev[offs[0]:offs[0] + sizes[0]]
+        fv = view(1, torch.float32)
+        iv = view(2, torch.int32)
         return descs, fv, iv, view(3, torch.int32), view(4, torch.int32), h2d

@@ -261,3 +261,55 @@ def test_cfg2_logits_loss_at_model_scale():
     worst = sorted(rep.items(), key=lambda kv: kv[1][0])[:5]
     print("worst gradient cosines", worst)
     assert all(v[0] > 0.98 for n, v in rep.items() if v[2] > 1e-7), worst
+
+
+def test_cuda_graph_replay_matches_eager():
+    """Graph mode: eager on first sight of a batch shape, capture on the second, replay afterwards -- with fresh data
+    every step the results must equal the eager engine bit for bit (same kernels, same order)."""
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    eager = make_policy(cfg, w)
+    graph = make_policy(cfg, w)
+    graph.use_cuda_graphs = True
+    base = small_batch("mixed", cfg.text_tokens)
+
+    def perturb(batch, k):
+        out = []
+        for s in batch:
+            d = {}
+            for key, v in s.items():
+                if isinstance(v, torch.Tensor) and v.dtype == torch.float32 and key != "images":
+                    d[key] = v * (1.0 + 0.1 * k)
+                else:
+                    d[key] = v
+            out.append(d)
+        return out
+
+    for k in range(4):   # eager, capture, replay, replay
+        batch = perturb(base, k)
+        for m in (eager, graph):
+            m.zero_grad()
+        le, loss_e = eager(batch, compute_loss=True)
+        loss_e.backward()
+        lg, loss_g = graph(batch, compute_loss=True)
+        loss_g.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(le, lg), k
+        assert loss_e.item() == loss_g.item(), k
+        for (n, pe), (_, pg) in zip(eager.named_parameters(), graph.named_parameters()):
+            if pe.grad is None:
+                assert pg.grad is None
+            else:
+                denom = pe.grad.abs().max().item() + 1e-12
+                assert (pe.grad - pg.grad).abs().max().item() <= 1e-5 * denom + 1e-9, (k, n)   # atomics reorder fp32 sums
+    assert any("fwd" in e for e in graph._graphs.values())
+    # gradient accumulation through the graphs
+    graph.zero_grad()
+    eager.zero_grad()
+    for _ in range(2):
+        _, l1 = eager(base, compute_loss=True); l1.backward()
+        _, l2 = graph(base, compute_loss=True); l2.backward()
+    torch.cuda.synchronize()
+    for (n, pe), (_, pg) in zip(eager.named_parameters(), graph.named_parameters()):
+        if pe.grad is not None:
+            assert (pe.grad - pg.grad).abs().max().item() <= 1e-5 * (pe.grad.abs().max().item() + 1e-12) + 1e-9, n
