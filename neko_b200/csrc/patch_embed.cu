@@ -1,14 +1,17 @@
 // Image patch embedding: ImageEmbedding.forward / ResidualBlock_V2 (embeddings.py:28-61,111-131).
 //
 //   x = (img/255*2 - 1)/sqrt(p)  ->  patchify 16x16  ->  h = conv1(GELU(x)) 3->C, 3x3, per-patch zero pad
-//   -> GroupNorm(groups) -> GELU -> conv2 C->3 -> x + .   -> flatten (c p1 p2) -> fp16 row of the projection GEMM
+//   -> GroupNorm(groups) -> GELU -> conv2 C->3 -> x + .   -> flatten (c p1 p2) -> 16-bit row of the projection GEMM
 //
-// One CTA processes one patch at a time (persistent loop over patches, weights resident in shared memory),
-// the C x 256 intermediate never leaves shared memory (the unfused torch path writes / re-reads 131 KB per
-// patch four times).  fp32 CUDA-core arithmetic; thread = (2x2 pixel quad, quarter of the channels) so each
-// weight fetched from shared memory feeds 4 FMAs.  Backward recomputes conv1 + GroupNorm from the saved
-// (mean, rstd), accumulates all weight gradients in registers / shared memory across the CTA's patches and
-// flushes once with atomics.
+// One CTA (8 warps) processes one patch at a time in a persistent loop with the weights resident in shared memory; the
+// C x 256 intermediate never leaves the SM (the unfused torch path writes / re-reads 131 KB per patch four times).
+// Both convolutions and all their gradients are small GEMMs on the tensor cores (mma.sync m16n8k16 bf16, fp32
+// accumulate) over im2col operands built in shared memory:
+//   conv1      H[px][c]      = colX[px][n] . W1[c][n]            n = (ci,ky,kx) + a ones column that carries the bias
+//   conv2      out[px][co]  += h2pad[px+tap][c] . W2[co][c][tap] nine shifted GEMMs over a zero-bordered pixel grid
+//   d conv2    dh2[px][c]    = colY[px][n] . W2r[c][n]           n = (co,tap), colY = im2col of dY
+//   wgrads     dW2r[n][c]   += colY^T . h2      dW1[c][n] += dh^T . colX     (K = 256 pixels; ones column => db1)
+// GroupNorm statistics / affine gradients are reduced with warp shuffles and per-warp shared-memory slots.
 #include "common.cuh"
 
 namespace neko {
@@ -16,9 +19,11 @@ namespace neko {
 constexpr int PE_P = 16;            // patch edge
 constexpr int PE_PX = 256;          // pixels per patch
 constexpr int PE_C = 128;           // mid channels (train.py always passes 128)
-constexpr int PE_THREADS = 256;
-constexpr int PE_HP = 257;          // hbuf pitch (odd: channel-owner sweeps are bank-conflict free)
+constexpr int PE_THREADS = 256;     // 8 warps: warp w owns pixels [32w, 32w+32) = image rows 2w, 2w+1
 constexpr int PE_PAD = 18;          // padded edge
+constexpr int PE_KP = 40;           // pitch of the K=32 im2col / weight tiles (80 bytes: conflict-free ldmatrix)
+constexpr int PE_CP = PE_C + 8;     // pitch of 128-channel tiles
+constexpr int PE_HP2 = 64 + 8;      // pitch of half-channel tiles (backward)
 
 struct PatchArgs {
   const void* images;
@@ -32,70 +37,60 @@ struct PatchArgs {
   float *dw1, *db1, *dgw, *dgb, *dw2, *db2;
 };
 
-// layout helpers: pixel (y,x) <-> plane index  sub*64 + quad   (sub = (y&1)*2 + (x&1), quad = (y>>1)*8 + (x>>1))
-__device__ __forceinline__ int plane_index(int y, int x) { return (((y & 1) << 1) | (x & 1)) * 64 + ((y >> 1) << 3) + (x >> 1); }
+// F16: the forward runs its operands in fp16 (values are O(1), 3 more mantissa bits); the backward, whose dY operand needs
+// bf16's range, runs everything in bf16.
+template <bool F16 = false>
+__device__ __forceinline__ void pe_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pe_ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void pe_ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void pe_ldsm2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
 
-struct PatchSmem {
-  float* hbuf;    // [C][HP]
-  float* w1s;     // [C][27]
-  float* w2s;     // [3][C][9]
-  float* b1s;     // [C]
-  float* gws;     // [C]
-  float* gbs;     // [C]
-  float* gx;      // [3][18][18] gelu(x), zero padded
-  float* xin;     // [3][256]    normalised x (standard pixel order)
-  float* red;     // [4][3][256] conv2 partial sums / scratch
-  float* gstat;   // [groups][2] sum, sumsq  -> mean, rstd
-  float* dypad;   // [3][18][18] (backward)
-  float* gsum;    // [groups][2] s1, s2 (backward)
-  float* dgacc;   // [C] dgamma accumulators (backward)
-  float* dbacc;   // [C]
-  float* db2acc;  // [4]
+// bf16 tile in shared memory with a run-time pitch (elements)
+struct STile {
+  uint32_t base;
+  int pitch;
+  __device__ __forceinline__ uint32_t addr(int r, int c) const { return base + (uint32_t)(r * pitch + c) * 2u; }
 };
-
-__device__ __forceinline__ PatchSmem carve(float* base, bool bwd) {
-  PatchSmem s;
-  float* p = base;
-  s.hbuf = p; p += PE_C * PE_HP;
-  s.w1s = p; p += PE_C * 27;
-  s.w2s = p; p += 3 * PE_C * 9;
-  s.b1s = p; p += PE_C;
-  s.gws = p; p += PE_C;
-  s.gbs = p; p += PE_C;
-  s.gx = p; p += 3 * PE_PAD * PE_PAD;
-  s.xin = p; p += 3 * PE_PX;
-  s.red = p; p += 4 * 3 * PE_PX;
-  s.gstat = p; p += 2 * 64;
-  s.dypad = p; p += bwd ? 3 * PE_PAD * PE_PAD : 0;
-  s.gsum = p; p += bwd ? 2 * 64 : 0;
-  s.dgacc = p; p += bwd ? PE_C : 0;
-  s.dbacc = p; p += bwd ? PE_C : 0;
-  s.db2acc = p;
-  return s;
+// A fragment (16 x 16) of a tile stored [m][k]
+__device__ __forceinline__ void fa_mk(const STile& t, int m0, int k0, int lane, uint32_t (&a)[4]) {
+  pe_ldsm4(t.addr(m0 + (lane & 15), k0 + ((lane >> 4) << 3)), a);
 }
-static size_t patch_smem_bytes(bool bwd) {
-  size_t n = (size_t)PE_C * PE_HP + PE_C * 27 + 3 * PE_C * 9 + 3 * PE_C + 3 * PE_PAD * PE_PAD + 3 * PE_PX + 4 * 3 * PE_PX + 128;
-  if (bwd) n += 3 * PE_PAD * PE_PAD + 128 + 2 * PE_C + 4;
-  return n * sizeof(float);
+// A fragment of a tile stored [k][m] (transposed load)
+__device__ __forceinline__ void fa_km(const STile& t, int k0, int m0, int lane, uint32_t (&a)[4]) {
+  pe_ldsm4t(t.addr(k0 + (lane & 7) + (((lane >> 4) & 1) << 3), m0 + (((lane >> 3) & 1) << 3)), a);
+}
+// B fragments of two adjacent n-tiles from a tile stored [n][k]
+__device__ __forceinline__ void fb_nk(const STile& t, int n0, int k0, int lane, uint32_t (&b)[4]) {
+  pe_ldsm4(t.addr(n0 + (lane & 7) + ((lane >> 4) << 3), k0 + (((lane >> 3) & 1) << 3)), b);
+}
+// B fragments of two adjacent n-tiles from a tile stored [k][n] (transposed load)
+__device__ __forceinline__ void fb_kn(const STile& t, int k0, int n0, int lane, uint32_t (&b)[4]) {
+  pe_ldsm4t(t.addr(k0 + (lane & 7) + (((lane >> 3) & 1) << 3), n0 + ((lane >> 4) << 3)), b);
 }
 
-__device__ __forceinline__ void load_weights(const PatchArgs& a, PatchSmem& s) {
-  for (int i = threadIdx.x; i < PE_C * 27; i += PE_THREADS) s.w1s[i] = a.w1[i];
-  for (int i = threadIdx.x; i < 3 * PE_C * 9; i += PE_THREADS) s.w2s[i] = a.w2[i];
-  for (int i = threadIdx.x; i < PE_C; i += PE_THREADS) {
-    s.b1s[i] = a.b1[i];
-    s.gws[i] = a.gw[i];
-    s.gbs[i] = a.gb[i];
-  }
-}
-
-// load + normalise one patch: xin (standard order) and gx = gelu(x) zero-padded
-__device__ __forceinline__ void load_patch(const PatchArgs& a, PatchSmem& s, int patch) {
+// ---- shared staging common to forward and backward -------------------------------------------------
+// load + normalise one patch: xin (fp32, standard pixel order) and gx = gelu(x) on a zero-bordered 18x18 grid
+__device__ __forceinline__ void pe_load_patch(const PatchArgs& a, float* gx, float* xin, int patch) {
   const int npp = a.n_h * a.n_w;
   const int n = patch / npp, r = patch - n * npp;
   const int ph = r / a.n_w, pw = r - ph * a.n_w;
-  for (int i = threadIdx.x; i < 3 * PE_PAD * PE_PAD; i += PE_THREADS) s.gx[i] = 0.f;
-  __syncthreads();
   const int t = threadIdx.x, y = t >> 4, x = t & 15;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -103,147 +98,201 @@ __device__ __forceinline__ void load_patch(const PatchArgs& a, PatchSmem& s, int
     float v = a.is_u8 ? (float)reinterpret_cast<const uint8_t*>(a.images)[idx] : reinterpret_cast<const float*>(a.images)[idx];
     v = v / 255.0f * 2.0f - 1.0f;   // embeddings.py:40
     v = v / 4.0f;                   // / sqrt(patch_size), :41
-    s.xin[c * PE_PX + t] = v;
-    s.gx[(c * PE_PAD + y + 1) * PE_PAD + x + 1] = gelu_erf(v);
+    if (xin) xin[c * PE_PX + t] = v;
+    gx[(c * PE_PAD + y + 1) * PE_PAD + x + 1] = gelu_erf(v);
   }
-  __syncthreads();
+}
+// im2col row of this thread's pixel: col[px][n] = grid[c3][y + dy(tap)][x + dx(tap)], n = c3*9 + tap; entry 27 = `one`
+template <bool FLIP, bool F16 = false>
+__device__ __forceinline__ void pe_im2col_row(const float* grid, bf16* col, float one) {
+  const int t = threadIdx.x, y = t >> 4, x = t & 15;
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = 2 * i + h;
+      if (n < 27) {
+        const int c3 = n / 9, tap = n - c3 * 9, ky = tap / 3, kx = tap - ky * 3;
+        // forward conv reads in[y+ky-1][x+kx-1]; its transpose reads dY[y-ky+1][x-kx+1]   (grid has a 1-pixel border)
+        v[h] = FLIP ? grid[(c3 * PE_PAD + y - ky + 2) * PE_PAD + x - kx + 2] : grid[(c3 * PE_PAD + y + ky) * PE_PAD + x + kx];
+      } else {
+        v[h] = (n == 27) ? one : 0.f;
+      }
+    }
+    w[i] = F16 ? pack_f16x2(v[0], v[1]) : pack_bf16x2(v[0], v[1]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(col + t * PE_KP);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
-// conv1 for this thread's quad and channel slice -> hbuf (raw, pre-GroupNorm)
-__device__ __forceinline__ void conv1_quad(PatchSmem& s, int quad, int slice) {
-  const int qy = quad >> 3, qx = quad & 7;
-  float win[3][4][4];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) win[c][r][k] = s.gx[(c * PE_PAD + 2 * qy + r) * PE_PAD + 2 * qx + k];
-  for (int cc = 0; cc < PE_C / 4; ++cc) {
-    const int c = slice * (PE_C / 4) + cc;
-    const float* w = s.w1s + c * 27;
-    const float b = s.b1s[c];
-    float o00 = b, o01 = b, o10 = b, o11 = b;
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float wv = w[(ci * 3 + ky) * 3 + kx];
-          o00 = fmaf(wv, win[ci][ky][kx], o00);
-          o01 = fmaf(wv, win[ci][ky][kx + 1], o01);
-          o10 = fmaf(wv, win[ci][ky + 1][kx], o10);
-          o11 = fmaf(wv, win[ci][ky + 1][kx + 1], o11);
-        }
-    float* h = s.hbuf + c * PE_HP + quad;
-    h[0] = o00; h[64] = o01; h[128] = o10; h[192] = o11;
-  }
-}
+// GroupNorm group of accumulator column (n-tile nt, lane quad index q): columns nt*8 + 2q, +1 -> group (nt*8 + 2q) / gs
+// (gs = 4 channels per group with the reference's 32 groups over 128 channels; any gs that is a multiple of 2 works)
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(PatchArgs a) {
-  extern __shared__ __align__(16) float pe_smem[];
-  PatchSmem s = carve(pe_smem, false);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int quad = tid & 63, slice = tid >> 6;
+  extern __shared__ __align__(16) uint8_t pe_raw[];
+  // carve
+  bf16* colX = reinterpret_cast<bf16*>(pe_raw);                       // [256][40]  (all forward tiles hold fp16 bit patterns)
+  bf16* W1s = colX + PE_PX * PE_KP;                                    // [128][40]   (n = 27 column holds the bias)
+  bf16* h2pad = W1s + PE_C * PE_KP;                                    // [324][136]  zero-bordered pixel grid
+  bf16* W2s = h2pad + PE_PAD * PE_PAD * PE_CP;                         // [9][8][136] rows co >= 3 are zero
+  float* gx = reinterpret_cast<float*>(W2s + 9 * 8 * PE_CP);           // [3][18][18]
+  float* xin = gx + 3 * PE_PAD * PE_PAD;                               // [3][256]
+  float* gpart = xin + 3 * PE_PX;                                      // [8 warps][64 groups][2]
+  float* gstat = gpart + 8 * 64 * 2;                                   // [64 groups][2] mean, rstd
+  float* gws = gstat + 128;                                            // [128]
+  float* gbs = gws + PE_C;                                             // [128]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int P = a.n_img * a.n_h * a.n_w;
-  const int gs = PE_C / a.groups;  // channels per group
-  load_weights(a, s);
+  const int gs = PE_C / a.groups;
+  const STile tX{(uint32_t)__cvta_generic_to_shared(colX), PE_KP}, tW1{(uint32_t)__cvta_generic_to_shared(W1s), PE_KP};
+  const STile tH{(uint32_t)__cvta_generic_to_shared(h2pad), PE_CP}, tW2{(uint32_t)__cvta_generic_to_shared(W2s), PE_CP};
+
+  // one-time: weights to bf16 tiles, zero borders
+  for (int i = tid; i < PE_C * PE_KP; i += PE_THREADS) {
+    const int c = i / PE_KP, n = i - c * PE_KP;
+    reinterpret_cast<__half*>(W1s)[i] = __float2half_rn(n < 27 ? a.w1[c * 27 + n] : (n == 27 ? a.b1[c] : 0.f));
+  }
+  for (int i = tid; i < 9 * 8 * PE_CP; i += PE_THREADS) {
+    const int tap = i / (8 * PE_CP), r = i - tap * 8 * PE_CP, co = r / PE_CP, c = r - co * PE_CP;
+    reinterpret_cast<__half*>(W2s)[i] = __float2half_rn((co < 3 && c < PE_C) ? a.w2[(co * PE_C + c) * 9 + tap] : 0.f);
+  }
+  for (int i = tid; i < PE_PAD * PE_PAD * PE_CP; i += PE_THREADS) h2pad[i] = __float2bfloat16_rn(0.f);
+  for (int i = tid; i < 3 * PE_PAD * PE_PAD; i += PE_THREADS) gx[i] = 0.f;
+  for (int i = tid; i < PE_C; i += PE_THREADS) { gws[i] = a.gw[i]; gbs[i] = a.gb[i]; }
+  __syncthreads();
+
   for (int patch = blockIdx.x; patch < P; patch += gridDim.x) {
-    load_patch(a, s, patch);
-    if (tid < 2 * a.groups) s.gstat[tid] = 0.f;
-    conv1_quad(s, quad, slice);
+    pe_load_patch(a, gx, xin, patch);
     __syncthreads();
-    // GroupNorm statistics (biased variance over gs channels x 256 pixels)
-    for (int g0 = 0; g0 < (PE_C / 4) / gs; ++g0) {
-      const int g = slice * ((PE_C / 4) / gs) + g0;
-      float sum = 0.f, sq = 0.f;
-      for (int k = 0; k < gs; ++k) {
-        const float* h = s.hbuf + (g * gs + k) * PE_HP + quad;
+    pe_im2col_row<false, true>(gx, colX, 1.0f);
+    __syncthreads();
+    // ---- conv1 (+bias): H[px][c], this warp's 32 pixels x 128 channels in registers ----
+    float h[2][16][4];
+    {
+      uint32_t ax[2][2][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const float v = h[u * 64]; sum += v; sq += v * v; }
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) fa_mk(tX, warp * 32 + mt * 16, k * 16, lane, ax[mt][k]);
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { h[mt][2 * n2][e] = 0.f; h[mt][2 * n2 + 1][e] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint32_t b[4];
+          fb_nk(tW1, n2 * 16, k * 16, lane, b);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            pe_mma<true>(h[mt][2 * n2], ax[mt][k], b[0], b[1]);
+            pe_mma<true>(h[mt][2 * n2 + 1], ax[mt][k], b[2], b[3]);
+          }
+        }
       }
-      sum = warp_sum(sum); sq = warp_sum(sq);
-      if (lane == 0) { atomicAdd(&s.gstat[2 * g], sum); atomicAdd(&s.gstat[2 * g + 1], sq); }
+    }
+    // ---- GroupNorm statistics: this thread's columns nt*8 + 2q, +1 belong to group (nt*8 + 2q) / gs ----
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float v = h[mt][nt][e]; s += v; ss += v * v; }
+      // reduce over the 8 row-lanes (g) -- and over the lanes of the same group inside the quad
+      s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 8); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      if (gs >= 4) { s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1); }
+      if (gs >= 8) { s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2); }
+      const int grp = (nt * 8 + 2 * q) / gs;
+      const bool owner = (g == 0) && ((2 * q) % (gs < 8 ? gs : 8) == 0);
+      if (owner) {  // per-warp slot: for gs >= 8 several n-tiles map to one group -> accumulate
+        float* slot = gpart + (warp * 64 + grp) * 2;
+        if (gs > 8 && (nt * 8) % gs != 0) { slot[0] += s; slot[1] += ss; } else { slot[0] = s; slot[1] = ss; }
+      }
     }
     __syncthreads();
     if (tid < a.groups) {
+      float s = 0.f, ss = 0.f;
+      for (int w = 0; w < 8; ++w) { s += gpart[(w * 64 + tid) * 2]; ss += gpart[(w * 64 + tid) * 2 + 1]; }
       const float n = (float)(gs * PE_PX);
-      const float mean = s.gstat[2 * tid] / n;
-      const float var = fmaxf(s.gstat[2 * tid + 1] / n - mean * mean, 0.f);
+      const float mean = s / n;
+      const float var = fmaxf(ss / n - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
-      s.gstat[2 * tid] = mean; s.gstat[2 * tid + 1] = rstd;
+      gstat[2 * tid] = mean; gstat[2 * tid + 1] = rstd;
       a.stats[((size_t)patch * a.groups + tid) * 2] = mean;
       a.stats[((size_t)patch * a.groups + tid) * 2 + 1] = rstd;
     }
     __syncthreads();
-    // normalise + GELU in place (own elements)
-    for (int cc = 0; cc < PE_C / 4; ++cc) {
-      const int c = slice * (PE_C / 4) + cc, g = c / gs;
-      const float mean = s.gstat[2 * g], rstd = s.gstat[2 * g + 1], gw = s.gws[c], gb = s.gbs[c];
-      float* h = s.hbuf + c * PE_HP + quad;
+    // ---- normalise + GELU -> h2pad (bf16), interior of the 18x18 grid ----
 #pragma unroll
-      for (int u = 0; u < 4; ++u) h[u * 64] = gelu_erf((h[u * 64] - mean) * rstd * gw + gb);
-    }
-    __syncthreads();
-    // conv2 partial sums over this slice's channels
-    const int qy = quad >> 3, qx = quad & 7;
-    int off[4][4];
+    for (int nt = 0; nt < 16; ++nt) {
+      const int c0 = nt * 8 + 2 * q;
+      const int grp = c0 / gs;
+      const float mean = gstat[2 * grp], rstd = gstat[2 * grp + 1];
+      const float w0 = gws[c0], w1 = gws[c0 + 1], b0 = gbs[c0], b1 = gbs[c0 + 1];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+      for (int mt = 0; mt < 2; ++mt) {
+        const int y = warp * 2 + mt;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int y = 2 * qy + r - 1, x = 2 * qx + k - 1;
-        off[r][k] = (y >= 0 && y < PE_P && x >= 0 && x < PE_P) ? plane_index(y, x) : -1;
-      }
-    float acc[3][4];
-#pragma unroll
-    for (int co = 0; co < 3; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.f;
-    for (int cc = 0; cc < PE_C / 4; ++cc) {
-      const int c = slice * (PE_C / 4) + cc;
-      const float* h = s.hbuf + c * PE_HP;
-      float win[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) win[r][k] = off[r][k] >= 0 ? h[off[r][k]] : 0.f;
-#pragma unroll
-      for (int co = 0; co < 3; ++co) {
-        const float* w = s.w2s + (co * PE_C + c) * 9;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float wv = w[ky * 3 + kx];
-            acc[co][0] = fmaf(wv, win[ky][kx], acc[co][0]);
-            acc[co][1] = fmaf(wv, win[ky][kx + 1], acc[co][1]);
-            acc[co][2] = fmaf(wv, win[ky + 1][kx], acc[co][2]);
-            acc[co][3] = fmaf(wv, win[ky + 1][kx + 1], acc[co][3]);
-          }
+        for (int hh = 0; hh < 2; ++hh) {
+          const int x = g + hh * 8;
+          const float v0 = gelu_erf((h[mt][nt][2 * hh] - mean) * rstd * w0 + b0);
+          const float v1 = gelu_erf((h[mt][nt][2 * hh + 1] - mean) * rstd * w1 + b1);
+          *reinterpret_cast<uint32_t*>(h2pad + ((y + 1) * PE_PAD + x + 1) * PE_CP + c0) = pack_f16x2(v0, v1);
+        }
       }
     }
-#pragma unroll
-    for (int co = 0; co < 3; ++co)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) s.red[(slice * 3 + co) * PE_PX + u * 64 + quad] = acc[co][u];
     __syncthreads();
-    // residual + bias, write the (c p1 p2) row
+    // ---- conv2: nine shifted GEMMs, M = this warp's two image rows, N = 8 (3 used), K = 128 ----
+    float o[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+      for (int k = 0; k < PE_C / 16; ++k) {
+        uint32_t b0, b1;
+        pe_ldsm2(tW2.addr(tap * 8 + (lane & 7), k * 16 + (((lane >> 3) & 1) << 3)), b0, b1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int y = warp * 2 + mt;
+          uint32_t af[4];
+          fa_mk(tH, (y + ky) * PE_PAD + kx, k * 16, lane, af);
+          pe_mma<true>(o[mt], af, b0, b1);
+        }
+      }
+    }
+    // ---- residual + bias, write the (c p1 p2) row: thread holds (x = g, g+8; co = 2q, 2q+1) ----
     {
-      const int y = tid >> 4, x = tid & 15, pi = plane_index(y, x);
-      uint16_t* o = a.out + (size_t)patch * (3 * PE_PX);
+      uint16_t* orow = a.out + (size_t)patch * (3 * PE_PX);
+      uint16_t* orow_b = a.out_bf ? a.out_bf + (size_t)patch * (3 * PE_PX) : nullptr;
 #pragma unroll
-      for (int co = 0; co < 3; ++co) {
-        float v = s.xin[co * PE_PX + tid] + a.b2[co];
+      for (int mt = 0; mt < 2; ++mt) {
+        const int y = warp * 2 + mt;
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) v += s.red[(sl * 3 + co) * PE_PX + pi];
-        o[co * PE_PX + tid] = cvt_16(v, true);
-        if (a.out_bf) a.out_bf[(size_t)patch * (3 * PE_PX) + co * PE_PX + tid] = cvt_16(v, false);
+        for (int e = 0; e < 4; ++e) {
+          const int co = 2 * q + (e & 1), x = g + (e >> 1) * 8;
+          if (co < 3) {
+            const int px = y * 16 + x;
+            const float v = xin[co * PE_PX + px] + a.b2[co] + o[mt][e];
+            orow[co * PE_PX + px] = cvt_16(v, true);
+            if (orow_b) orow_b[co * PE_PX + px] = cvt_16(v, false);
+          }
+        }
       }
     }
-    __syncthreads();
+    __syncthreads();  // gx / xin / colX / h2pad are rewritten by the next patch
   }
 }
 
@@ -251,169 +300,239 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(Patch
 // backward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(PatchArgs a) {
-  extern __shared__ __align__(16) float pe_smem[];
-  PatchSmem s = carve(pe_smem, true);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int quad = tid & 63, slice = tid >> 6;
-  const int qy = quad >> 3, qx = quad & 7;
+  extern __shared__ __align__(16) uint8_t pe_raw[];
+  bf16* colX = reinterpret_cast<bf16*>(pe_raw);                       // [256][40] im2col of gelu(x) (+ ones column)
+  bf16* colY = colX + PE_PX * PE_KP;                                   // [256][40] flipped im2col of dY
+  bf16* W1s = colY + PE_PX * PE_KP;                                    // [128][40]
+  bf16* W2r = W1s + PE_C * PE_KP;                                      // [128][40]  W2r[c][co*9+tap] = w2[co][c][tap]
+  bf16* h2s = W2r + PE_C * PE_KP;                                      // [256][72]  gelu(gn(h)) of the current channel half
+  bf16* dhs = h2s + PE_PX * PE_HP2;                                    // [256][72]  gradient at the conv1 output
+  float* gx = reinterpret_cast<float*>(dhs + PE_PX * PE_HP2);          // [3][18][18]
+  float* dyp = gx + 3 * PE_PAD * PE_PAD;                               // [3][18][18]
+  float* gpart = dyp + 3 * PE_PAD * PE_PAD;                            // [8 warps][64 groups][2]  s1, s2 partials
+  float* gstat = gpart + 8 * 64 * 2;                                   // [64][2] mean, rstd
+  float* gsum = gstat + 128;                                           // [64][2] m1, m2
+  float* gws = gsum + 128;                                             // [128]
+  float* gbs = gws + PE_C;                                             // [128]
+  float* aff = gbs + PE_C;                                             // [8 warps][128][2] dgamma, dbeta accumulators
+  float* db2s = aff + 8 * PE_C * 2;                                    // [8 warps][4]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int P = a.n_img * a.n_h * a.n_w;
   const int gs = PE_C / a.groups;
-  // channel-owner mapping for the weight gradients: channel oc, taps [n0, n1)
-  const int oc = tid & (PE_C - 1), half = tid >> 7;
-  const int n0 = half ? 14 : 0, n1 = half ? 27 : 14;
-  float dw2acc[14], dw1acc[14];
-#pragma unroll
-  for (int i = 0; i < 14; ++i) dw2acc[i] = dw1acc[i] = 0.f;
-  float db1acc = 0.f;
-  // shared-memory offsets of this thread's taps (entry 13 of the upper half duplicates tap 26 and is dropped at the flush)
-  int doff[14], goff[14];
-#pragma unroll
-  for (int j = 0; j < 14; ++j) {
-    const int n = min(n0 + j, 26);
-    const int c3 = n / 9, tap = n - c3 * 9, ky = tap / 3, kx = tap - ky * 3;
-    doff[j] = (c3 * PE_PAD + 2 - ky) * PE_PAD + 2 - kx;   // dY[co][y-ky+1][x-kx+1] in the padded tile
-    goff[j] = (c3 * PE_PAD + ky) * PE_PAD + kx;           // gelu(x)[ci][y+ky-1][x+kx-1] in the padded tile
+  const STile tX{(uint32_t)__cvta_generic_to_shared(colX), PE_KP}, tY{(uint32_t)__cvta_generic_to_shared(colY), PE_KP};
+  const STile tW1{(uint32_t)__cvta_generic_to_shared(W1s), PE_KP}, tW2{(uint32_t)__cvta_generic_to_shared(W2r), PE_KP};
+  const STile tH2{(uint32_t)__cvta_generic_to_shared(h2s), PE_HP2}, tDH{(uint32_t)__cvta_generic_to_shared(dhs), PE_HP2};
+
+  for (int i = tid; i < PE_C * PE_KP; i += PE_THREADS) {
+    const int c = i / PE_KP, n = i - c * PE_KP;
+    W1s[i] = __float2bfloat16_rn(n < 27 ? a.w1[c * 27 + n] : (n == 27 ? a.b1[c] : 0.f));
+    float w2v = 0.f;
+    if (n < 27) { const int co = n / 9, tap = n - co * 9; w2v = a.w2[(co * PE_C + c) * 9 + tap]; }
+    W2r[i] = __float2bfloat16_rn(w2v);
   }
-  load_weights(a, s);
-  for (int i = tid; i < PE_C; i += PE_THREADS) { s.dgacc[i] = 0.f; s.dbacc[i] = 0.f; }
-  if (tid < 4) s.db2acc[tid] = 0.f;
+  for (int i = tid; i < 3 * PE_PAD * PE_PAD; i += PE_THREADS) { gx[i] = 0.f; dyp[i] = 0.f; }
+  for (int i = tid; i < PE_C; i += PE_THREADS) { gws[i] = a.gw[i]; gbs[i] = a.gb[i]; }
+  for (int i = tid; i < 8 * PE_C * 2; i += PE_THREADS) aff[i] = 0.f;
+  if (tid < 32) db2s[tid] = 0.f;
+  __syncthreads();
+
+  // weight-gradient accumulators, persistent over this CTA's patches.
+  // dW2r[n][c]: per channel half 2 (n m-tiles) x 8 (c n-tiles) output tiles -> warp w owns m-tile (w & 1), n-tiles 2*(w>>1), +1
+  // dW1 [c][n]: per channel half 4 (c m-tiles) x 4 (n n-tiles) output tiles -> warp w owns m-tile (w >> 1), n-tiles 2*(w&1), +1
+  float aw2[2][2][4], aw1[2][2][4];
+#pragma unroll
+  for (int hc = 0; hc < 2; ++hc)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { aw2[hc][j][e] = 0.f; aw1[hc][j][e] = 0.f; }
 
   for (int patch = blockIdx.x; patch < P; patch += gridDim.x) {
-    load_patch(a, s, patch);
-    for (int i = tid; i < 3 * PE_PAD * PE_PAD; i += PE_THREADS) s.dypad[i] = 0.f;
-    if (tid < a.groups) {
-      s.gstat[2 * tid] = a.stats[((size_t)patch * a.groups + tid) * 2];
-      s.gstat[2 * tid + 1] = a.stats[((size_t)patch * a.groups + tid) * 2 + 1];
-    }
-    if (tid < 2 * a.groups) s.gsum[tid] = 0.f;
-    __syncthreads();
+    pe_load_patch(a, gx, nullptr, patch);
     {
       const int y = tid >> 4, x = tid & 15;
-      const bf16* g = a.dout + (size_t)patch * (3 * PE_PX);
+      const bf16* gy = a.dout + (size_t)patch * (3 * PE_PX);
 #pragma unroll
       for (int co = 0; co < 3; ++co) {
-        const float v = __bfloat162float(g[co * PE_PX + tid]);
-        s.dypad[(co * PE_PAD + y + 1) * PE_PAD + x + 1] = v;
+        const float v = __bfloat162float(gy[co * PE_PX + tid]);
+        dyp[(co * PE_PAD + y + 1) * PE_PAD + x + 1] = v;
         const float t = warp_sum(v);
-        if (lane == 0) atomicAdd(&s.db2acc[co], t);
+        if (lane == 0) db2s[warp * 4 + co] += t;
       }
     }
-    conv1_quad(s, quad, slice);
+    if (tid < a.groups) {
+      gstat[2 * tid] = a.stats[((size_t)patch * a.groups + tid) * 2];
+      gstat[2 * tid + 1] = a.stats[((size_t)patch * a.groups + tid) * 2 + 1];
+    }
+    __syncthreads();
+    pe_im2col_row<false>(gx, colX, 1.0f);
+    pe_im2col_row<true>(dyp, colY, 0.0f);
     __syncthreads();
 
-    // ---- dW2[co][oc][tap] += sum_px h2[oc][px] * dY[co][px - tap + 1] ----
-    {
-      const int g = oc / gs;
-      const float mean = s.gstat[2 * g], rstd = s.gstat[2 * g + 1], gw = s.gws[oc], gb = s.gbs[oc];
-      const float* h = s.hbuf + oc * PE_HP;
-      for (int i = 0; i < PE_PX; ++i) {
-        const int sub = i >> 6, q = i & 63;
-        const int y = 2 * (q >> 3) + (sub >> 1), x = 2 * (q & 7) + (sub & 1);
-        const float h2 = gelu_erf((h[i] - mean) * rstd * gw + gb);
-        const int base = y * PE_PAD + x;
+    uint32_t ax[2][2][4], ay[2][2][4];
 #pragma unroll
-        for (int j = 0; j < 14; ++j) dw2acc[j] = fmaf(h2, s.dypad[doff[j] + base], dw2acc[j]);
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        fa_mk(tX, warp * 32 + mt * 16, k * 16, lane, ax[mt][k]);
+        fa_mk(tY, warp * 32 + mt * 16, k * 16, lane, ay[mt][k]);
       }
-    }
-    // ---- pass A: dh2 -> dhn, group sums, dgamma / dbeta ----
-    float dyw[3][4][4];
+
 #pragma unroll
-    for (int co = 0; co < 3; ++co)
+    for (int hc = 0; hc < 2; ++hc) {
+      // ---- recompute conv1 and run the transposed conv2 for 64 channels: H, dh2 [32 px][64 c] per warp ----
+      float h[2][8][4], dh[2][8][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int n2 = 0; n2 < 4; ++n2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dyw[co][r][k] = s.dypad[(co * PE_PAD + 2 * qy + r) * PE_PAD + 2 * qx + k];
-    auto dh2_of = [&](int c, float (&d)[4]) {
-      d[0] = d[1] = d[2] = d[3] = 0.f;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int co = 0; co < 3; ++co) {
-        const float* w = s.w2s + (co * PE_C + c) * 9;
+          for (int e = 0; e < 4; ++e) { h[mt][2 * n2][e] = h[mt][2 * n2 + 1][e] = 0.f; dh[mt][2 * n2][e] = dh[mt][2 * n2 + 1][e] = 0.f; }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int k = 0; k < 2; ++k) {
+          uint32_t b1f[4], b2f[4];
+          fb_nk(tW1, hc * 64 + n2 * 16, k * 16, lane, b1f);
+          fb_nk(tW2, hc * 64 + n2 * 16, k * 16, lane, b2f);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float wv = w[ky * 3 + kx];
-            // pixel (y,x) receives w[ky][kx] * dY[y-ky+1][x-kx+1]; window origin is (2qy-1, 2qx-1)
-            d[0] = fmaf(wv, dyw[co][2 - ky][2 - kx], d[0]);
-            d[1] = fmaf(wv, dyw[co][2 - ky][3 - kx], d[1]);
-            d[2] = fmaf(wv, dyw[co][3 - ky][2 - kx], d[2]);
-            d[3] = fmaf(wv, dyw[co][3 - ky][3 - kx], d[3]);
+          for (int mt = 0; mt < 2; ++mt) {
+            pe_mma(h[mt][2 * n2], ax[mt][k], b1f[0], b1f[1]);
+            pe_mma(h[mt][2 * n2 + 1], ax[mt][k], b1f[2], b1f[3]);
+            pe_mma(dh[mt][2 * n2], ay[mt][k], b2f[0], b2f[1]);
+            pe_mma(dh[mt][2 * n2 + 1], ay[mt][k], b2f[2], b2f[3]);
+          }
+        }
+      }
+      // ---- elementwise: xhat, h2 = gelu(hn) -> h2s ; dhn = dh2 * gelu'(hn) ; group partial sums ; dgamma / dbeta ----
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c0 = hc * 64 + nt * 8 + 2 * q;
+        const int grp = c0 / gs;
+        const float mean = gstat[2 * grp], rstd = gstat[2 * grp + 1];
+        const float w0 = gws[c0], w1 = gws[c0 + 1], b0 = gbs[c0], b1 = gbs[c0 + 1];
+        float s1 = 0.f, s2 = 0.f, dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int px = warp * 32 + mt * 16 + g + hh * 8;
+            const float xh0 = (h[mt][nt][2 * hh] - mean) * rstd, xh1 = (h[mt][nt][2 * hh + 1] - mean) * rstd;
+            const float hn0 = xh0 * w0 + b0, hn1 = xh1 * w1 + b1;
+            *reinterpret_cast<uint32_t*>(h2s + px * PE_HP2 + nt * 8 + 2 * q) = pack_bf16x2(gelu_erf(hn0), gelu_erf(hn1));
+            const float d0 = dh[mt][nt][2 * hh] * gelu_erf_grad(hn0), d1 = dh[mt][nt][2 * hh + 1] * gelu_erf_grad(hn1);
+            h[mt][nt][2 * hh] = xh0; h[mt][nt][2 * hh + 1] = xh1;     // keep xhat
+            dh[mt][nt][2 * hh] = d0; dh[mt][nt][2 * hh + 1] = d1;     // keep dhn
+            dg0 += d0 * xh0; dg1 += d1 * xh1; db0 += d0; db1 += d1;
+          }
+        s1 = w0 * db0 + w1 * db1;
+        s2 = w0 * dg0 + w1 * dg1;
+        // per-channel sums over this warp's pixels (reduce over g), per-group sums additionally over the quad lanes
+#pragma unroll
+        for (int m = 4; m <= 16; m <<= 1) {
+          dg0 += __shfl_xor_sync(0xffffffffu, dg0, m); dg1 += __shfl_xor_sync(0xffffffffu, dg1, m);
+          db0 += __shfl_xor_sync(0xffffffffu, db0, m); db1 += __shfl_xor_sync(0xffffffffu, db1, m);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, m); s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        }
+        if (gs >= 4) { s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1); }
+        if (gs >= 8) { s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2); }
+        if (g == 0) {
+          float* af = aff + (warp * PE_C + c0) * 2;
+          af[0] += dg0; af[1] += db0; af[2] += dg1; af[3] += db1;
+          if ((2 * q) % (gs < 8 ? gs : 8) == 0) {
+            float* slot = gpart + (warp * 64 + grp) * 2;
+            if (gs > 8 && (nt * 8) % gs != 0) { slot[0] += s1; slot[1] += s2; } else { slot[0] = s1; slot[1] = s2; }
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < a.groups) {
+        const int lo = (hc * 64) / gs, hi = (hc * 64 + 64) / gs;
+        if (tid >= lo && tid < hi) {
+          float s1 = 0.f, s2 = 0.f;
+          for (int w = 0; w < 8; ++w) { s1 += gpart[(w * 64 + tid) * 2]; s2 += gpart[(w * 64 + tid) * 2 + 1]; }
+          const float inv_n = 1.0f / (float)(gs * PE_PX);
+          gsum[2 * tid] = s1 * inv_n; gsum[2 * tid + 1] = s2 * inv_n;
+        }
+      }
+      __syncthreads();
+      // ---- dh = rstd * (gamma * dhn - m1 - xhat * m2) -> dhs (bf16) ----
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c0 = hc * 64 + nt * 8 + 2 * q;
+        const int grp = c0 / gs;
+        const float rstd = gstat[2 * grp + 1], m1 = gsum[2 * grp], m2 = gsum[2 * grp + 1];
+        const float w0 = gws[c0], w1 = gws[c0 + 1];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int px = warp * 32 + mt * 16 + g + hh * 8;
+            const float v0 = rstd * (w0 * dh[mt][nt][2 * hh] - m1 - h[mt][nt][2 * hh] * m2);
+            const float v1 = rstd * (w1 * dh[mt][nt][2 * hh + 1] - m1 - h[mt][nt][2 * hh + 1] * m2);
+            *reinterpret_cast<uint32_t*>(dhs + px * PE_HP2 + nt * 8 + 2 * q) = pack_bf16x2(v0, v1);
           }
       }
-    };
-    for (int g0 = 0; g0 < (PE_C / 4) / gs; ++g0) {
-      const int g = slice * ((PE_C / 4) / gs) + g0;
-      const float mean = s.gstat[2 * g], rstd = s.gstat[2 * g + 1];
-      float s1 = 0.f, s2 = 0.f;
-      for (int k = 0; k < gs; ++k) {
-        const int c = g * gs + k;
-        const float gw = s.gws[c], gb = s.gbs[c];
-        float d[4];
-        dh2_of(c, d);
-        const float* h = s.hbuf + c * PE_HP + quad;
-        float dg = 0.f, db = 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float xh = (h[u * 64] - mean) * rstd;
-          const float dhn = d[u] * gelu_erf_grad(xh * gw + gb);
-          dg += dhn * xh; db += dhn;
-        }
-        s1 += gw * db; s2 += gw * dg;
-        dg = warp_sum(dg); db = warp_sum(db);
-        if (lane == 0) { atomicAdd(&s.dgacc[c], dg); atomicAdd(&s.dbacc[c], db); }
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) { atomicAdd(&s.gsum[2 * g], s1); atomicAdd(&s.gsum[2 * g + 1], s2); }
-    }
-    __syncthreads();
-    // ---- pass B: dh (gradient at the conv1 output) written over hbuf ----
-    {
-      const float inv_n = 1.0f / (float)(gs * PE_PX);
-      for (int cc = 0; cc < PE_C / 4; ++cc) {
-        const int c = slice * (PE_C / 4) + cc, g = c / gs;
-        const float mean = s.gstat[2 * g], rstd = s.gstat[2 * g + 1], gw = s.gws[c], gb = s.gbs[c];
-        const float m1 = s.gsum[2 * g] * inv_n, m2 = s.gsum[2 * g + 1] * inv_n;
-        float d[4];
-        dh2_of(c, d);
-        float* h = s.hbuf + c * PE_HP + quad;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float xh = (h[u * 64] - mean) * rstd;
-          const float dhn = d[u] * gelu_erf_grad(xh * gw + gb);
-          h[u * 64] = rstd * (gw * dhn - m1 - xh * m2);
+      __syncthreads();
+      // ---- weight gradients over K = 256 pixels ----
+      {
+        const int mt2 = warp & 1, nb2 = (warp >> 1) * 16;   // dW2r tile: n rows [16*mt2, +16), channels [nb2, +16) of this half
+        const int mt1 = warp >> 1, nb1 = (warp & 1) * 16;   // dW1  tile: channels [16*mt1, +16) of this half, n cols [nb1, +16)
+#pragma unroll 4
+        for (int k = 0; k < PE_PX / 16; ++k) {
+          uint32_t af[4], bfr[4];
+          fa_km(tY, k * 16, mt2 * 16, lane, af);
+          fb_kn(tH2, k * 16, nb2, lane, bfr);
+          pe_mma(aw2[hc][0], af, bfr[0], bfr[1]);
+          pe_mma(aw2[hc][1], af, bfr[2], bfr[3]);
+          fa_km(tDH, k * 16, mt1 * 16, lane, af);
+          fb_kn(tX, k * 16, nb1, lane, bfr);
+          pe_mma(aw1[hc][0], af, bfr[0], bfr[1]);
+          pe_mma(aw1[hc][1], af, bfr[2], bfr[3]);
         }
       }
+      __syncthreads();  // h2s / dhs are rewritten by the next half / patch
     }
-    __syncthreads();
-    // ---- dW1[oc][ci][tap] += sum_px dh[oc][px] * gelu(x)[ci][px + tap - 1];  db1[oc] += sum_px dh ----
-    {
-      const float* h = s.hbuf + oc * PE_HP;
-      for (int i = 0; i < PE_PX; ++i) {
-        const int sub = i >> 6, q = i & 63;
-        const int y = 2 * (q >> 3) + (sub >> 1), x = 2 * (q & 7) + (sub & 1);
-        const float dh = h[i];
-        if (half == 0) db1acc += dh;
-        const int base = y * PE_PAD + x;
+  }
+
+  // ---- flush the CTA's gradient partials ----
 #pragma unroll
-        for (int j = 0; j < 14; ++j) dw1acc[j] = fmaf(dh, s.gx[goff[j] + base], dw1acc[j]);
+  for (int hc = 0; hc < 2; ++hc)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        {  // dW2r[n][c] -> d_conv2_w[co][c][tap]
+          const int n = (warp & 1) * 16 + g + (e >> 1) * 8;
+          const int c = hc * 64 + (warp >> 1) * 16 + j * 8 + 2 * q + (e & 1);
+          if (n < 27) { const int co = n / 9, tap = n - co * 9; atomicAdd(a.dw2 + ((size_t)co * PE_C + c) * 9 + tap, aw2[hc][j][e]); }
+        }
+        {  // dW1[c][n] -> d_conv1_w[c][ci][tap] ; column 27 (ones) is the bias gradient
+          const int c = hc * 64 + (warp >> 1) * 16 + g + (e >> 1) * 8;
+          const int n = (warp & 1) * 16 + j * 8 + 2 * q + (e & 1);
+          if (n < 27) atomicAdd(a.dw1 + (size_t)c * 27 + n, aw1[hc][j][e]);
+          else if (n == 27) atomicAdd(a.db1 + c, aw1[hc][j][e]);
+        }
       }
-    }
-    __syncthreads();
-  }
-  // flush
-#pragma unroll
-  for (int j = 0; j < 14; ++j) {
-    const int n = n0 + j;
-    if (n < n1) {
-      const int co = n / 9, tap = n - co * 9;
-      atomicAdd(a.dw2 + ((size_t)co * PE_C + oc) * 9 + tap, dw2acc[j]);
-      atomicAdd(a.dw1 + (size_t)oc * 27 + n, dw1acc[j]);
-    }
-  }
-  if (half == 0) atomicAdd(a.db1 + oc, db1acc);
   __syncthreads();
-  for (int i = tid; i < PE_C; i += PE_THREADS) { atomicAdd(a.dgw + i, s.dgacc[i]); atomicAdd(a.dgb + i, s.dbacc[i]); }
-  if (tid < 3) atomicAdd(a.db2 + tid, s.db2acc[tid]);
+  for (int c = tid; c < PE_C; c += PE_THREADS) {
+    float dg = 0.f, db = 0.f;
+    for (int w = 0; w < 8; ++w) { dg += aff[(w * PE_C + c) * 2]; db += aff[(w * PE_C + c) * 2 + 1]; }
+    atomicAdd(a.dgw + c, dg);
+    atomicAdd(a.dgb + c, db);
+  }
+  if (tid < 3) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += db2s[w * 4 + tid];
+    atomicAdd(a.db2 + tid, s);
+  }
+}
+
+static size_t patch_smem_bytes(bool bwd) {
+  if (!bwd)
+    return (size_t)(PE_PX * PE_KP + PE_C * PE_KP + PE_PAD * PE_PAD * PE_CP + 9 * 8 * PE_CP) * 2 +
+           (size_t)(3 * PE_PAD * PE_PAD + 3 * PE_PX + 8 * 64 * 2 + 128 + 2 * PE_C) * 4;
+  return (size_t)(2 * PE_PX * PE_KP + 2 * PE_C * PE_KP + 2 * PE_PX * PE_HP2) * 2 +
+         (size_t)(2 * 3 * PE_PAD * PE_PAD + 8 * 64 * 2 + 128 + 128 + 2 * PE_C + 8 * PE_C * 2 + 32) * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -453,7 +572,7 @@ __global__ void __launch_bounds__(256) patch_pos_bwd_kernel(const float* __restr
 static int check_patch_args(int n_img, int Himg, int Wimg, int patch, int C, int groups) {
   NEKO_REQUIRE(patch == PE_P, "patch_resblock: only patch_size 16 is implemented (got %d)", patch);
   NEKO_REQUIRE(C == PE_C, "patch_resblock: only resid_mid_channels 128 is implemented (got %d)", C);
-  NEKO_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / 4) % (C / groups) == 0, "patch_resblock: unsupported num_groups %d", groups);
+  NEKO_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0 && 64 % (C / groups) == 0, "patch_resblock: unsupported num_groups %d", groups);
   NEKO_REQUIRE(n_img > 0 && Himg > 0 && Wimg > 0 && Himg % patch == 0 && Wimg % patch == 0, "Image dimensions must be divisible by patch size");
   return NEKO_OK;
 }

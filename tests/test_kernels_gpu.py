@@ -318,3 +318,71 @@ def test_adamw_clip(ops):
         ops.sumsq(g, ss)
         ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, ss, 1.0)
     assert (p - pr.detach()).abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# image patch ResNet block (embeddings.py:28-61,111-131)
+# ---------------------------------------------------------------------------------------------------
+def _patch_block_torch(img, w1, b1, gw, gb, w2, b2, groups):
+    import torch.nn.functional as F
+    n, _, H, W = img.shape
+    x = (img.float() / 255.0 * 2 - 1) / 4.0
+    x = x.view(n, 3, H // 16, 16, W // 16, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 3, 16, 16)
+    h = F.conv2d(F.gelu(x), w1, b1, padding=1)
+    h = F.gelu(F.group_norm(h, groups, gw, gb, eps=1e-5))
+    return (x + F.conv2d(h, w2, b2, padding=1)).reshape(x.shape[0], -1)
+
+
+@pytest.mark.parametrize("groups", [32, 16, 8, 64])
+@pytest.mark.parametrize("u8", [True, False])
+def test_patch_resblock(ops, groups, u8):
+    import ctypes as C
+    from neko_b200 import _lib
+    from neko_b200.ops import _p, stream_ptr
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(7 + groups)
+    n, H, W, Cm = 5, 48, 64, 128
+    img = torch.randint(0, 256, (n, 3, H, W), generator=g, dtype=torch.uint8)
+    img = (img if u8 else img.float() + 0.25).cuda()
+    w1 = _rand((Cm, 3, 3, 3), 1, 0.3); b1 = _rand((Cm,), 2, 0.2)
+    gw = 1.0 + _rand((Cm,), 3, 0.2); gb = _rand((Cm,), 4, 0.2)
+    w2 = _rand((3, Cm, 3, 3), 5, 0.05); b2 = _rand((3,), 6, 0.1)
+    P = n * (H // 16) * (W // 16)
+    out16 = torch.empty(P, 768, dtype=torch.float16, device="cuda")
+    outbf = torch.empty(P, 768, dtype=torch.bfloat16, device="cuda")
+    stats = torch.empty(P, groups, 2, device="cuda")
+    _lib.check(lib.neko_patch_resblock_fwd(_p(img), C.c_int(int(u8)), C.c_int(n), C.c_int(H), C.c_int(W), C.c_int(16), C.c_int(Cm),
+                                           C.c_int(groups), _p(w1), _p(b1), _p(gw), _p(gb), _p(w2), _p(b2), _p(out16), _p(outbf),
+                                           _p(stats), stream_ptr()), "fwd")
+    params = [t.clone().requires_grad_(True) for t in (w1, b1, gw, gb, w2, b2)]
+    ref = _patch_block_torch(img, *params, groups)
+    err = (out16.float() - ref).abs().max().item()
+    assert err < 6e-3, err                      # bf16 conv operands, fp32 accumulation; outputs are O(0.3)
+    assert ((outbf.float() - ref).abs() - ref.abs() * 2.0 ** -8).max().item() < 6e-3
+    # GroupNorm statistics of the conv1 output
+    with torch.no_grad():
+        import torch.nn.functional as F
+        x = (img.float() / 255.0 * 2 - 1) / 4.0
+        x = x.view(n, 3, H // 16, 16, W // 16, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 3, 16, 16)
+        hh = F.conv2d(F.gelu(x), w1, b1, padding=1).view(P, groups, -1)
+        assert (stats[..., 0] - hh.mean(-1)).abs().max().item() < 2e-3
+        assert ((stats[..., 1] - (hh.var(-1, unbiased=False) + 1e-5).rsqrt()) / stats[..., 1]).abs().max().item() < 2e-2
+    # backward
+    dy = _rand((P, 768), 9, 1.0, torch.bfloat16)
+    ref.backward(dy.float())
+    grads = [torch.zeros_like(t) for t in (w1, b1, gw, gb, w2, b2)]
+    _lib.check(lib.neko_patch_resblock_bwd(_p(img), C.c_int(int(u8)), C.c_int(n), C.c_int(H), C.c_int(W), C.c_int(16), C.c_int(Cm),
+                                           C.c_int(groups), _p(w1), _p(b1), _p(gw), _p(gb), _p(w2), _p(stats), _p(dy),
+                                           _p(grads[0]), _p(grads[1]), _p(grads[2]), _p(grads[3]), _p(grads[4]), _p(grads[5]),
+                                           stream_ptr()), "bwd")
+    for name, got, p in zip(("w1", "b1", "gw", "gb", "w2", "b2"), grads, params):
+        want = p.grad
+        rel = ((got - want).norm() / want.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
+        assert rel < 2e-2 and cos > 0.9995, (name, rel, cos)
+    # gradients accumulate into their destination
+    _lib.check(lib.neko_patch_resblock_bwd(_p(img), C.c_int(int(u8)), C.c_int(n), C.c_int(H), C.c_int(W), C.c_int(16), C.c_int(Cm),
+                                           C.c_int(groups), _p(w1), _p(b1), _p(gw), _p(gb), _p(w2), _p(stats), _p(dy),
+                                           _p(grads[0]), _p(grads[1]), _p(grads[2]), _p(grads[3]), _p(grads[4]), _p(grads[5]),
+                                           stream_ptr()), "bwd")
+    assert ((grads[0] - 2 * params[0].grad).norm() / params[0].grad.norm()).item() < 4e-2

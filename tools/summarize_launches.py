@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, total and share.
-Only the LAST step is counted when a step marker (tokenize_embed_kernel) is present."""
+One period (step) of the launch sequence is counted, delimited by the tokenize_embed_kernel marker."""
 import csv
 import sys
 from collections import OrderedDict
@@ -17,11 +17,9 @@ for r in csv.DictReader(lines):
 # keep the launches of the last step
 starts = [i for i, r in enumerate(rows) if "tokenize_embed" in r[0]]
 if len(starts) >= 2:
-    # the cast of the weights precedes tokenize; include it
-    s = starts[-1]
-    while s > 0 and ("cast_f32" in rows[s - 1][0]):
-        s -= 1
-    rows = rows[s:]
+    # one period of the launch sequence: from the previous step's tokenize marker up to this step's (the image-embedding
+    # and weight-cast launches that precede the marker belong to the period's tail; every step launches the same list)
+    rows = rows[starts[-2]:starts[-1]]
 agg = OrderedDict()
 for k, ns, _g in rows:
     name = k.split("(")[0]
