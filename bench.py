@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--head", default="dense", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
+    ap.add_argument("--head", default="rows", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
     ap.add_argument("--lean", action="store_true", help="evaluate the LM head on loss rows only (forward returns no logits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step from CUDA graphs")

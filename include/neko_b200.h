@@ -167,6 +167,7 @@ int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t*
  * ------------------------------------------------------------------------------------------- */
 #define NEKO_CE_LOGITS_COMPACT 1   /* logits row r (not rows[r]) holds position rows[r]            */
 #define NEKO_CE_DLOGITS_COMPACT 2  /* dlogits row r (not rows[r]) receives position rows[r]         */
+#define NEKO_CE_ZERO_PAD 4         /* bwd also zeroes dlogits columns V..ld_dlogits of the rows it writes */
 int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
                        const int64_t* tokens, float* row_lse, float* row_loss, float* loss, int flags,
                        void* stream);

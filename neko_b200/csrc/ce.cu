@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
   }
   for (int i = start + threadIdx.x; i < V; i += CE_THREADS)
     dz[i] = __float2bfloat16_rn((__expf(z[i] - lse) - (i == tgt ? 1.f : 0.f)) * g);
+  if (flags & NEKO_CE_ZERO_PAD)  // pad columns V..ld feed the K tail of the head dgrad GEMM
+    for (long long i = V + threadIdx.x; i < ldd; i += CE_THREADS) dz[i] = __float2bfloat16_rn(0.f);
 }
 
 }  // namespace neko

@@ -56,24 +56,51 @@ __device__ __forceinline__ float erf_fast(float x) {
   const float y = 1.0f - p * t * __expf(-a * a);
   return copysignf(y, x);
 }
+// ---- GELU (exact-erf form, nn.GELU default) on the same A&S 7.1.26 kernel, arranged for instruction count ----
+// h(x) = Phi(-|x|) = 0.5 erfc(|x| / sqrt2) = t (a1' + t (a2' + ...)) e,  t = 1 / (1 + p |x| / sqrt2),  e = exp(-x^2 / 2)
+// (coefficients pre-multiplied by 0.5).  13 instructions per GELU incl. one MUFU.RCP and one MUFU.EX2; the .ftz
+// forms skip libdevice's denormal fix-ups (arguments are >= 1 resp. results below 2^-126 flush to the correct 0).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gelu_tail(float x, float& e) {
+  const float t = rcp_ftz(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  const float k = x * 0.84932180028801904272f;   // sqrt(log2(e) / 2):  exp(-x^2/2) = 2^(-k^2)
+  e = ex2_ftz(-k * k);
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return p * t * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
+  float e;
+  const float h = gelu_tail(x, e);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.0f));      // x >= 0: x (1 - h);  x < 0: x h
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float h = gelu_tail(x, e);
+  const float cdf = x >= 0.0f ? 1.0f - h : h;
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+// value and derivative from one evaluation of the tail
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float e;
+  const float h = gelu_tail(x, e);
+  y = fmaf(-fabsf(x), h, fmaxf(x, 0.0f));
+  dy = fmaf(x * 0.39894228040143267794f, e, x >= 0.0f ? 1.0f - h : h);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// fp16 conversions saturate at the largest finite half instead of overflowing to inf
+// fp16 conversions saturate at the largest finite half instead of overflowing to inf (one F2FP.SATFINITE)
 __device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // 16-bit pair in the requested format (f16 = IEEE half, else bfloat16)
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }

@@ -776,7 +776,9 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   const bool can_split = (epilogue == NEKO_EPI_F32) && (bias == nullptr);
   // CTA pairs pay off where the main loop dominates (measured per shape, profiles/r01_gemm_shapes.md): plain fp32
   // outputs (LM head, weight gradients) and wide 16-bit outputs; narrow-N and epilogue-heavy launches stay single-CTA.
-  int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (epilogue == NEKO_EPI_BF16 && N >= 2048)) ? 1 : 0;
+  // (tools/gemm_sweep.py: at K >= 2048 the 256 x 256 pair tile also wins for N = 768 despite filling only 1.2 waves.)
+  const bool plain16 = (epilogue == NEKO_EPI_BF16), resid = (epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_RESID_F32_BF16);
+  int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (plain16 && (N >= 2048 || K >= 2048)) || (resid && K >= 2048)) ? 1 : 0;
   if (const char* force = getenv("NEKO_GEMM_PAIR")) { pair_lo = pair_hi = atoi(force) ? 1 : 0; }
   double best = 1e30;
   p.BN = 128; p.splits = 1; p.pair = 0;
@@ -785,7 +787,7 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     const int workers = pr ? sms / 2 : sms;
     for (int bn = 128; bn <= 256; bn += 128) {
       if (bn == 256 && N <= 128) break;
-      const double kb_cost = pr ? (bn == 128 ? 0.95 : 1.5) : (bn == 128 ? 1.15 : 2.0);
+      const double kb_cost = pr ? (bn == 128 ? 1.15 : 1.4) : (bn == 128 ? 1.15 : 1.6);   // fitted to tools/gemm_sweep.py
       const long long tiles_ = mb_ * ((N + bn - 1) / bn);
       for (int sp = 1; sp <= (can_split ? 16 : 1); ++sp) {
         if (sp > 1 && kblocks / sp < 8) break;

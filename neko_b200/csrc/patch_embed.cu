@@ -134,14 +134,19 @@ __device__ __forceinline__ void pe_im2col_row(const float* grid, bf16* col, floa
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(PatchArgs a) {
+// Two CTAs per SM.  conv1 is cheap (K = 32), so it runs twice instead of holding the 256 x 128 tile in registers:
+// pass A accumulates the GroupNorm sums, pass B recomputes 16 channels at a time, normalises, applies GELU and feeds
+// the result -- already in the A-fragment layout -- straight into  Z[px][(co,tap)] += h2[px][c] W2[(co,tap)][c].
+// conv2's output is then a 9-tap shifted gather of Z through shared memory.
+constexpr int PE_ZP = 260;          // pitch (floats) of the transposed Z tile: conflict-free fragment stores and row reads
+
+__global__ void __launch_bounds__(PE_THREADS, 2) patch_resblock_fwd_kernel(PatchArgs a) {
   extern __shared__ __align__(16) uint8_t pe_raw[];
-  // carve
   bf16* colX = reinterpret_cast<bf16*>(pe_raw);                       // [256][40]  (all forward tiles hold fp16 bit patterns)
-  bf16* W1s = colX + PE_PX * PE_KP;                                    // [128][40]   (n = 27 column holds the bias)
-  bf16* h2pad = W1s + PE_C * PE_KP;                                    // [324][136]  zero-bordered pixel grid
-  bf16* W2s = h2pad + PE_PAD * PE_PAD * PE_CP;                         // [9][8][136] rows co >= 3 are zero
-  float* gx = reinterpret_cast<float*>(W2s + 9 * 8 * PE_CP);           // [3][18][18]
+  bf16* W1s = colX + PE_PX * PE_KP;                                    // [128][40]  (n = 27 column holds the bias)
+  bf16* W2n = W1s + PE_C * PE_KP;                                      // [32][136]  W2n[co*9+tap][c], rows >= 27 zero
+  float* Zs = reinterpret_cast<float*>(W2n + 32 * PE_CP);              // [32][260]  Z transposed: [(co,tap)][px]
+  float* gx = Zs + 32 * PE_ZP;                                         // [3][18][18]
   float* xin = gx + 3 * PE_PAD * PE_PAD;                               // [3][256]
   float* gpart = xin + 3 * PE_PX;                                      // [8 warps][64 groups][2]
   float* gstat = gpart + 8 * 64 * 2;                                   // [64 groups][2] mean, rstd
@@ -150,22 +155,23 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(Patch
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int P = a.n_img * a.n_h * a.n_w;
-  const int gs = PE_C / a.groups;
+  const int gs = PE_C / a.groups, gshift = 31 - __clz(gs);             // channels per group: a power of two in [2, 64]
   const STile tX{(uint32_t)__cvta_generic_to_shared(colX), PE_KP}, tW1{(uint32_t)__cvta_generic_to_shared(W1s), PE_KP};
-  const STile tH{(uint32_t)__cvta_generic_to_shared(h2pad), PE_CP}, tW2{(uint32_t)__cvta_generic_to_shared(W2s), PE_CP};
+  const STile tW2{(uint32_t)__cvta_generic_to_shared(W2n), PE_CP};
 
-  // one-time: weights to bf16 tiles, zero borders
   for (int i = tid; i < PE_C * PE_KP; i += PE_THREADS) {
     const int c = i / PE_KP, n = i - c * PE_KP;
     reinterpret_cast<__half*>(W1s)[i] = __float2half_rn(n < 27 ? a.w1[c * 27 + n] : (n == 27 ? a.b1[c] : 0.f));
   }
-  for (int i = tid; i < 9 * 8 * PE_CP; i += PE_THREADS) {
-    const int tap = i / (8 * PE_CP), r = i - tap * 8 * PE_CP, co = r / PE_CP, c = r - co * PE_CP;
-    reinterpret_cast<__half*>(W2s)[i] = __float2half_rn((co < 3 && c < PE_C) ? a.w2[(co * PE_C + c) * 9 + tap] : 0.f);
+  for (int i = tid; i < 32 * PE_CP; i += PE_THREADS) {
+    const int n = i / PE_CP, c = i - n * PE_CP;
+    float v = 0.f;
+    if (n < 27 && c < PE_C) { const int co = n / 9, tap = n - co * 9; v = a.w2[(co * PE_C + c) * 9 + tap]; }
+    reinterpret_cast<__half*>(W2n)[i] = __float2half_rn(v);
   }
-  for (int i = tid; i < PE_PAD * PE_PAD * PE_CP; i += PE_THREADS) h2pad[i] = __float2bfloat16_rn(0.f);
   for (int i = tid; i < 3 * PE_PAD * PE_PAD; i += PE_THREADS) gx[i] = 0.f;
   for (int i = tid; i < PE_C; i += PE_THREADS) { gws[i] = a.gw[i]; gbs[i] = a.gb[i]; }
+  const float b2r[3] = {a.b2[0], a.b2[1], a.b2[2]};
   __syncthreads();
 
   for (int patch = blockIdx.x; patch < P; patch += gridDim.x) {
@@ -173,126 +179,140 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_fwd_kernel(Patch
     __syncthreads();
     pe_im2col_row<false, true>(gx, colX, 1.0f);
     __syncthreads();
-    // ---- conv1 (+bias): H[px][c], this warp's 32 pixels x 128 channels in registers ----
-    float h[2][16][4];
-    {
-      uint32_t ax[2][2][4];
+    uint32_t ax[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) fa_mk(tX, warp * 32 + mt * 16, k * 16, lane, ax[mt][k]);
+
+    // conv1 (+bias) of this warp's 32 pixels for channels [16 n2, 16 n2 + 16)
+    auto conv1 = [&](int n2, float (&h)[2][2][4]) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int k = 0; k < 2; ++k) fa_mk(tX, warp * 32 + mt * 16, k * 16, lane, ax[mt][k]);
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int n2 = 0; n2 < 8; ++n2) {
+          for (int e = 0; e < 4; ++e) h[mt][j][e] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t b[4];
+        fb_nk(tW1, n2 * 16, k * 16, lane, b);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          pe_mma<true>(h[mt][0], ax[mt][k], b[0], b[1]);
+          pe_mma<true>(h[mt][1], ax[mt][k], b[2], b[3]);
+        }
+      }
+    };
+
+    // ---- pass A: GroupNorm sums.  Columns nt*8 + 2q, +1 of this thread belong to group (nt*8 + 2q) >> gshift ----
+#pragma unroll 2
+    for (int n2 = 0; n2 < 8; ++n2) {
+      float h[2][2][4];
+      conv1(n2, h);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int nt = 2 * n2 + j;
+        float s = 0.f, ss = 0.f;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { h[mt][2 * n2][e] = 0.f; h[mt][2 * n2 + 1][e] = 0.f; }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          uint32_t b[4];
-          fb_nk(tW1, n2 * 16, k * 16, lane, b);
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            pe_mma<true>(h[mt][2 * n2], ax[mt][k], b[0], b[1]);
-            pe_mma<true>(h[mt][2 * n2 + 1], ax[mt][k], b[2], b[3]);
-          }
+          for (int e = 0; e < 4; ++e) { const float v = h[mt][j][e]; s += v; ss = fmaf(v, v, ss); }
+        s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        if (gs >= 4) { s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1); }
+        if (gs >= 8) { s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2); }
+        if (g == 0 && ((2 * q) & (min(gs, 8) - 1)) == 0) {   // one owner lane per (n-tile, group)
+          float* slot = gpart + (warp * 64 + ((nt * 8 + 2 * q) >> gshift)) * 2;
+          if ((nt * 8) & (gs - 1)) { slot[0] += s; slot[1] += ss; } else { slot[0] = s; slot[1] = ss; }   // gs > 8: several n-tiles per group
         }
-      }
-    }
-    // ---- GroupNorm statistics: this thread's columns nt*8 + 2q, +1 belong to group (nt*8 + 2q) / gs ----
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { const float v = h[mt][nt][e]; s += v; ss += v * v; }
-      // reduce over the 8 row-lanes (g) -- and over the lanes of the same group inside the quad
-      s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 8); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-      if (gs >= 4) { s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1); }
-      if (gs >= 8) { s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2); }
-      const int grp = (nt * 8 + 2 * q) / gs;
-      const bool owner = (g == 0) && ((2 * q) % (gs < 8 ? gs : 8) == 0);
-      if (owner) {  // per-warp slot: for gs >= 8 several n-tiles map to one group -> accumulate
-        float* slot = gpart + (warp * 64 + grp) * 2;
-        if (gs > 8 && (nt * 8) % gs != 0) { slot[0] += s; slot[1] += ss; } else { slot[0] = s; slot[1] = ss; }
       }
     }
     __syncthreads();
     if (tid < a.groups) {
       float s = 0.f, ss = 0.f;
+#pragma unroll
       for (int w = 0; w < 8; ++w) { s += gpart[(w * 64 + tid) * 2]; ss += gpart[(w * 64 + tid) * 2 + 1]; }
-      const float n = (float)(gs * PE_PX);
-      const float mean = s / n;
-      const float var = fmaxf(ss / n - mean * mean, 0.f);
+      const float inv_n = 1.0f / (float)(gs * PE_PX);
+      const float mean = s * inv_n;
+      const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
       gstat[2 * tid] = mean; gstat[2 * tid + 1] = rstd;
       a.stats[((size_t)patch * a.groups + tid) * 2] = mean;
       a.stats[((size_t)patch * a.groups + tid) * 2 + 1] = rstd;
     }
     __syncthreads();
-    // ---- normalise + GELU -> h2pad (bf16), interior of the 18x18 grid ----
+
+    // ---- pass B: recompute 16 channels, normalise + GELU, Z += h2 . W2n^T ----
+    float z[2][4][4];
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      const int c0 = nt * 8 + 2 * q;
-      const int grp = c0 / gs;
-      const float mean = gstat[2 * grp], rstd = gstat[2 * grp + 1];
-      const float w0 = gws[c0], w1 = gws[c0 + 1], b0 = gbs[c0], b1 = gbs[c0 + 1];
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int y = warp * 2 + mt;
+      for (int n = 0; n < 4; ++n)
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int x = g + hh * 8;
-          const float v0 = gelu_erf((h[mt][nt][2 * hh] - mean) * rstd * w0 + b0);
-          const float v1 = gelu_erf((h[mt][nt][2 * hh + 1] - mean) * rstd * w1 + b1);
-          *reinterpret_cast<uint32_t*>(h2pad + ((y + 1) * PE_PAD + x + 1) * PE_CP + c0) = pack_f16x2(v0, v1);
-        }
-      }
-    }
-    __syncthreads();
-    // ---- conv2: nine shifted GEMMs, M = this warp's two image rows, N = 8 (3 used), K = 128 ----
-    float o[2][4];
+        for (int e = 0; e < 4; ++e) z[mt][n][e] = 0.f;
+#pragma unroll 2
+    for (int kt = 0; kt < 8; ++kt) {
+      float h[2][2][4];
+      conv1(kt, h);
+      uint32_t af[2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ky = tap / 3, kx = tap - ky * 3;
-#pragma unroll
-      for (int k = 0; k < PE_C / 16; ++k) {
-        uint32_t b0, b1;
-        pe_ldsm2(tW2.addr(tap * 8 + (lane & 7), k * 16 + (((lane >> 3) & 1) << 3)), b0, b1);
+      for (int j = 0; j < 2; ++j) {
+        const int c0 = kt * 16 + j * 8 + 2 * q;
+        const int grp = c0 >> gshift;
+        const float mean = gstat[2 * grp], rstd = gstat[2 * grp + 1];
+        const float w0 = gws[c0] * rstd, w1 = gws[c0 + 1] * rstd;
+        const float o0 = fmaf(-mean, w0, gbs[c0]), o1 = fmaf(-mean, w1, gbs[c0 + 1]);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          const int y = warp * 2 + mt;
-          uint32_t af[4];
-          fa_mk(tH, (y + ky) * PE_PAD + kx, k * 16, lane, af);
-          pe_mma<true>(o[mt], af, b0, b1);
+          // C fragment (rows g / g+8, columns 2q, 2q+1 of n-tile j)  ==  A fragment registers 2j (row g), 2j+1 (row g+8)
+          af[mt][2 * j] = pack_f16x2(gelu_erf(fmaf(h[mt][j][0], w0, o0)), gelu_erf(fmaf(h[mt][j][1], w1, o1)));
+          af[mt][2 * j + 1] = pack_f16x2(gelu_erf(fmaf(h[mt][j][2], w0, o0)), gelu_erf(fmaf(h[mt][j][3], w1, o1)));
+        }
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        uint32_t b[4];
+        fb_nk(tW2, n2 * 16, kt * 16, lane, b);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          pe_mma<true>(z[mt][2 * n2], af[mt], b[0], b[1]);
+          pe_mma<true>(z[mt][2 * n2 + 1], af[mt], b[2], b[3]);
         }
       }
     }
-    // ---- residual + bias, write the (c p1 p2) row: thread holds (x = g, g+8; co = 2q, 2q+1) ----
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          Zs[(n * 8 + 2 * q + (e & 1)) * PE_ZP + warp * 32 + mt * 16 + g + (e >> 1) * 8] = z[mt][n][e];
+    __syncthreads();
+    // ---- conv2 = 9-tap shifted gather of Z, + residual + bias; thread = pixel, coalesced (c p1 p2) rows ----
     {
+      const int y = tid >> 4, x = tid & 15;
+      float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if ((unsigned)(y + dy) < 16u && (unsigned)(x + dx) < 16u) {
+#pragma unroll
+          for (int co = 0; co < 3; ++co) o[co] += Zs[(co * 9 + tap) * PE_ZP + tid + dy * 16 + dx];
+        }
+      }
       uint16_t* orow = a.out + (size_t)patch * (3 * PE_PX);
       uint16_t* orow_b = a.out_bf ? a.out_bf + (size_t)patch * (3 * PE_PX) : nullptr;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int y = warp * 2 + mt;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int co = 2 * q + (e & 1), x = g + (e >> 1) * 8;
-          if (co < 3) {
-            const int px = y * 16 + x;
-            const float v = xin[co * PE_PX + px] + a.b2[co] + o[mt][e];
-            orow[co * PE_PX + px] = cvt_16(v, true);
-            if (orow_b) orow_b[co * PE_PX + px] = cvt_16(v, false);
-          }
-        }
+      for (int co = 0; co < 3; ++co) {
+        const float v = xin[co * PE_PX + tid] + b2r[co] + o[co];
+        orow[co * PE_PX + tid] = cvt_16(v, true);
+        if (orow_b) orow_b[co * PE_PX + tid] = cvt_16(v, false);
       }
     }
-    __syncthreads();  // gx / xin / colX / h2pad are rewritten by the next patch
+    // (the next iteration's writes to gx / xin / colX / gpart / Zs are each separated from this iteration's last
+    //  read of the same buffer by at least one of the barriers above)
   }
 }
 
@@ -319,7 +339,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int P = a.n_img * a.n_h * a.n_w;
-  const int gs = PE_C / a.groups;
+  const int gs = PE_C / a.groups, gshift = 31 - __clz(gs);             // channels per group: a power of two in [2, 64]
   const STile tX{(uint32_t)__cvta_generic_to_shared(colX), PE_KP}, tY{(uint32_t)__cvta_generic_to_shared(colY), PE_KP};
   const STile tW1{(uint32_t)__cvta_generic_to_shared(W1s), PE_KP}, tW2{(uint32_t)__cvta_generic_to_shared(W2r), PE_KP};
   const STile tH2{(uint32_t)__cvta_generic_to_shared(h2s), PE_HP2}, tDH{(uint32_t)__cvta_generic_to_shared(dhs), PE_HP2};
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int c0 = hc * 64 + nt * 8 + 2 * q;
-        const int grp = c0 / gs;
+        const int grp = c0 >> gshift;
         const float mean = gstat[2 * grp], rstd = gstat[2 * grp + 1];
         const float w0 = gws[c0], w1 = gws[c0 + 1], b0 = gbs[c0], b1 = gbs[c0 + 1];
         float s1 = 0.f, s2 = 0.f, dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
@@ -418,8 +438,11 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
             const int px = warp * 32 + mt * 16 + g + hh * 8;
             const float xh0 = (h[mt][nt][2 * hh] - mean) * rstd, xh1 = (h[mt][nt][2 * hh + 1] - mean) * rstd;
             const float hn0 = xh0 * w0 + b0, hn1 = xh1 * w1 + b1;
-            *reinterpret_cast<uint32_t*>(h2s + px * PE_HP2 + nt * 8 + 2 * q) = pack_bf16x2(gelu_erf(hn0), gelu_erf(hn1));
-            const float d0 = dh[mt][nt][2 * hh] * gelu_erf_grad(hn0), d1 = dh[mt][nt][2 * hh + 1] * gelu_erf_grad(hn1);
+            float y0, y1, g0, g1;
+            gelu_erf_both(hn0, y0, g0);
+            gelu_erf_both(hn1, y1, g1);
+            *reinterpret_cast<uint32_t*>(h2s + px * PE_HP2 + nt * 8 + 2 * q) = pack_bf16x2(y0, y1);
+            const float d0 = dh[mt][nt][2 * hh] * g0, d1 = dh[mt][nt][2 * hh + 1] * g1;
             h[mt][nt][2 * hh] = xh0; h[mt][nt][2 * hh + 1] = xh1;     // keep xhat
             dh[mt][nt][2 * hh] = d0; dh[mt][nt][2 * hh + 1] = d1;     // keep dhn
             dg0 += d0 * xh0; dg1 += d1 * xh1; db0 += d0; db1 += d1;
@@ -438,15 +461,15 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
         if (g == 0) {
           float* af = aff + (warp * PE_C + c0) * 2;
           af[0] += dg0; af[1] += db0; af[2] += dg1; af[3] += db1;
-          if ((2 * q) % (gs < 8 ? gs : 8) == 0) {
+          if (((2 * q) & (min(gs, 8) - 1)) == 0) {
             float* slot = gpart + (warp * 64 + grp) * 2;
-            if (gs > 8 && (nt * 8) % gs != 0) { slot[0] += s1; slot[1] += s2; } else { slot[0] = s1; slot[1] = s2; }
+            if ((nt * 8) & (gs - 1)) { slot[0] += s1; slot[1] += s2; } else { slot[0] = s1; slot[1] = s2; }
           }
         }
       }
       __syncthreads();
       if (tid < a.groups) {
-        const int lo = (hc * 64) / gs, hi = (hc * 64 + 64) / gs;
+        const int lo = (hc * 64) >> gshift, hi = (hc * 64 + 64) >> gshift;
         if (tid >= lo && tid < hi) {
           float s1 = 0.f, s2 = 0.f;
           for (int w = 0; w < 8; ++w) { s1 += gpart[(w * 64 + tid) * 2]; s2 += gpart[(w * 64 + tid) * 2 + 1]; }
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int c0 = hc * 64 + nt * 8 + 2 * q;
-        const int grp = c0 / gs;
+        const int grp = c0 >> gshift;
         const float rstd = gstat[2 * grp + 1], m1 = gsum[2 * grp], m2 = gsum[2 * grp + 1];
         const float w0 = gws[c0], w1 = gws[c0 + 1];
 #pragma unroll
@@ -529,8 +552,8 @@ __global__ void __launch_bounds__(PE_THREADS, 1) patch_resblock_bwd_kernel(Patch
 
 static size_t patch_smem_bytes(bool bwd) {
   if (!bwd)
-    return (size_t)(PE_PX * PE_KP + PE_C * PE_KP + PE_PAD * PE_PAD * PE_CP + 9 * 8 * PE_CP) * 2 +
-           (size_t)(3 * PE_PAD * PE_PAD + 3 * PE_PX + 8 * 64 * 2 + 128 + 2 * PE_C) * 4;
+    return (size_t)(PE_PX * PE_KP + PE_C * PE_KP + 32 * PE_CP) * 2 +
+           (size_t)(32 * PE_ZP + 3 * PE_PAD * PE_PAD + 3 * PE_PX + 8 * 64 * 2 + 128 + 2 * PE_C) * 4;
   return (size_t)(2 * PE_PX * PE_KP + 2 * PE_C * PE_KP + 2 * PE_PX * PE_HP2) * 2 +
          (size_t)(2 * 3 * PE_PAD * PE_PAD + 8 * 64 * 2 + 128 + 128 + 2 * PE_C + 8 * PE_C * 2 + 32) * 4;
 }
@@ -572,7 +595,8 @@ __global__ void __launch_bounds__(256) patch_pos_bwd_kernel(const float* __restr
 static int check_patch_args(int n_img, int Himg, int Wimg, int patch, int C, int groups) {
   NEKO_REQUIRE(patch == PE_P, "patch_resblock: only patch_size 16 is implemented (got %d)", patch);
   NEKO_REQUIRE(C == PE_C, "patch_resblock: only resid_mid_channels 128 is implemented (got %d)", C);
-  NEKO_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0 && 64 % (C / groups) == 0, "patch_resblock: unsupported num_groups %d", groups);
+  NEKO_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0 && 64 % (C / groups) == 0 && ((C / groups) & (C / groups - 1)) == 0,
+               "patch_resblock: unsupported num_groups %d", groups);
   NEKO_REQUIRE(n_img > 0 && Himg > 0 && Wimg > 0 && Himg % patch == 0 && Wimg % patch == 0, "Image dimensions must be divisible by patch size");
   return NEKO_OK;
 }
@@ -596,7 +620,7 @@ int neko_patch_resblock_fwd(const void* images, int is_u8, int n_img, int Himg, 
   cudaError_t e = cudaFuncSetAttribute(patch_resblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(patch_fwd)");
   const int P = n_img * a.n_h * a.n_w;
-  const int grid = P < sm_count() ? P : sm_count();
+  const int grid = P < 2 * sm_count() ? P : 2 * sm_count();   // two resident CTAs per SM
   patch_resblock_fwd_kernel<<<grid, PE_THREADS, smem, as_stream(stream)>>>(a);
   NEKO_LAUNCH_CHECK("patch_resblock_fwd_kernel");
   return NEKO_OK;

@@ -137,7 +137,7 @@ def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[in
 # ------------------------------------------------------------------------------------------
 # masked cross entropy
 # ------------------------------------------------------------------------------------------
-CE_LOGITS_COMPACT, CE_DLOGITS_COMPACT = 1, 2
+CE_LOGITS_COMPACT, CE_DLOGITS_COMPACT, CE_ZERO_PAD = 1, 2, 4
 
 
 def masked_ce_fwd(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torch.Tensor, flags: int = 0):

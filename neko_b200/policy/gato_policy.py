@@ -241,7 +241,9 @@ class GatoPolicy(nn.Module):
         object.__setattr__(self.transformer, "_owner", ref)
         object.__setattr__(self.image_embedding, "_owner", ref)
         # engine knobs
-        self.head_mode = "dense"        # 'dense' | 'rows' (identical results; 'rows' compacts the loss rows in backward)
+        # head backward: 'rows' runs the LM-head weight / input gradients on the loss rows only (the other rows of dlogits
+        # are exactly zero); 'dense' runs them over every position like the reference's autograd.  Identical gradients.
+        self.head_mode = "rows"
         self.materialize_logits = True  # False: head evaluated on loss rows only, forward returns logits=None
         # 16-bit format of the FORWARD operands (activations fed to GEMMs, weight copy).  fp16 has 3 more mantissa
         # bits than bf16 at the same tensor-core rate and brings logits max-abs error from 2.1e-2 to ~6e-3 at
@@ -867,16 +869,18 @@ class GatoPolicy(nn.Module):
         compact_logits = not self.materialize_logits
         if self.head_mode == "rows" or compact_logits:
             dl = self._buf("dlogits_rows", (n_rows, Vp), torch.bfloat16)
-            if n_rows * Vp:
-                dl.zero_()  # pad columns V..Vp must be zero (K tail of the dgrad GEMM)
-            flags = ops.CE_DLOGITS_COMPACT | (ops.CE_LOGITS_COMPACT if compact_logits else 0)
+            # the kernel also zeroes the pad columns V..Vp (K tail of the dgrad GEMM)
+            flags = ops.CE_DLOGITS_COMPACT | ops.CE_ZERO_PAD | (ops.CE_LOGITS_COMPACT if compact_logits else 0)
             ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl, flags=flags)
             hc = self._buf("hf_rows_b", (n_rows, d), torch.bfloat16)
             ops.gather_rows(st.hf, st.loss_rows, d, hc)
             ops.gemm(dl, hc, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,
                      M=V, N=d, K=n_rows)
+            # K = the padded vocabulary (818 k-blocks), a handful of output tiles: fp32 output lets the kernel split K
+            dhc32 = self._buf("dhf_rows_f32", (n_rows, d), torch.float32)
+            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_F32, out=dhc32, M=n_rows, N=d, K=Vp)
             dhc = self._buf("dhf_rows", (n_rows, d), torch.bfloat16)
-            ops.gemm(dl, Wb("predict_token.weight", rows=Vp), b_mn=True, epilogue=ops.EPI_BF16, out=dhc, M=n_rows, N=d, K=Vp)
+            ops.cast_bf16(dhc32, dhc)
             dhf = self._buf("dhf", (N, d), torch.bfloat16)
             dhf.zero_()
             ops.scatter_rows(dhc, st.loss_rows, d, dhf)
