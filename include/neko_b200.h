@@ -36,6 +36,26 @@ int neko_device_check(void);
 int neko_sm_count(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dropout (nn.Dropout at trajectory_gpt2.py:179 attention weights, :254 and :278 residual branches, :707
+ * embeddings; p = --dropout, and 0.1 for the embeddings whatever --dropout says).  Masks are counter based: the keep
+ * decision of element (row, col) of site `stream` is a pure function of (seed, stream, row, col), so backward kernels
+ * regenerate them.  `seed` points to two uint32 words in DEVICE memory that the host refreshes before every forward
+ * (a replayed CUDA graph therefore draws fresh masks).  NULL pointer, NULL seed or thr16 == 0 disable dropout.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint32_t* seed;  /* device pointer to 2 words                                        */
+  uint32_t stream;       /* site id: 0 embeddings, 4*layer+1 attention, +2 attn residual, +3 mlp residual */
+  uint32_t thr16;        /* round(p * 65536): an element is dropped when its 16 random bits < thr16   */
+  float scale;           /* 65536 / (65536 - thr16), applied to kept elements                */
+  uint32_t reserved;
+} neko_dropout;
+
+/* x[rows, cols] (fp32, row pitch ld) *= mask * scale, in place.  Used for embd dropout and its backward. */
+int neko_dropout_apply(float* x, int64_t ld, int rows, int cols, const neko_dropout* drop, void* stream);
+/* keep[rows, cols] (uint8 0/1): the mask the kernels use -- for tests and for replaying a step in a reference. */
+int neko_dropout_mask(uint8_t* keep, int rows, int cols, const neko_dropout* drop, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tokenise + embed + interleave: GatoPolicy.tokenize_input_dicts, gato_policy.py:195-432,
  * with ContinuousTokenizer.encode / mu_law (input_tokenizers.py:5-30) inlined.
  * One descriptor per sample; the host packs all continuous values into `fvals`, all integer
@@ -98,10 +118,12 @@ int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, ui
                        float eps, int out_f16, void* stream);
 /* dx_resid (fp32 [N,d]) += LN'(dy); optional bf16 copy of the updated dx_resid; dgamma/dbeta
  * fp32 [d] are accumulated (caller zeroes them).  dx_colsum (nullable, fp32 [d], accumulated): column sums
- * of the updated dx_resid = the bias gradient of the Conv1D whose output was added into this residual. */
+ * of the bf16 copy = the bias gradient of the Conv1D whose output was added into this residual.
+ * branch_drop (nullable): the residual branch that produced x went through dropout (x = x_prev + dropout(branch)); the
+ * bf16 copy and dx_colsum then carry mask * scale * dx_resid, i.e. the gradient entering that branch. */
 int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean,
                        const float* rstd, float* dx_resid, uint16_t* dx_bf16, float* dgamma,
-                       float* dbeta, float* dx_colsum, int N, int d, void* stream);
+                       float* dbeta, float* dx_colsum, int N, int d, const neko_dropout* branch_drop, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense GEMM on tcgen05 tensor cores (HF Conv1D addmm trajectory_gpt2.py:222,253,274,277;
@@ -142,6 +164,7 @@ typedef struct neko_gemm_desc {
   void* C3; int64_t ldc3;       /* optional bf16 copy of C2 (GELU epilogue): the wgrad operand   */
   const float* bias;            /* [N] or NULL                                                  */
   const void* aux; int64_t ld_aux;
+  neko_dropout drop;            /* RESID epilogues: C = aux + dropout(acc + bias) (resid_dropout, trajectory_gpt2.py:254,278) */
 } neko_gemm_desc;
 
 int neko_gemm(const neko_gemm_desc* host_desc, void* stream);
@@ -152,14 +175,15 @@ int neko_gemm(const neko_gemm_desc* host_desc, void* stream);
  * qkv bf16 [B,S,3*H*dh] (q | k | v as c_attn emits them), out bf16 [B,S,H*dh], lse fp32 [B,H,S].
  * Sample b attends keys in [first_valid[b], min(query, S_valid-1)]; rows outside [first_valid[b], S_valid)
  * (left padding, right padding of --pad_seq) are written as zeros.
- * ------------------------------------------------------------------------------------------- */
+ * drop (nullable): attn_dropout on the softmax weights (:179); mask element (row = (b*H + h)*S + query, col = key).
+ */
 int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out,
                        uint16_t* out2_bf16 /* nullable second copy */, float* lse, int B, int S, int S_valid,
-                       int H, int dh, int out_f16, void* stream);
+                       int H, int dh, int out_f16, const neko_dropout* drop, void* stream);
 /* dqkv bf16 [B,S,3*H*dh]; delta fp32 [B,H,S] is caller-provided scratch. */
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse,
                        const int32_t* first_valid, uint16_t* dqkv, float* delta, int B, int S, int S_valid,
-                       int H, int dh, int out_f16, void* stream);
+                       int H, int dh, int out_f16, const neko_dropout* drop, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Masked cross entropy (gato_policy.py:174-186).  rows int32 [n_rows]: flat source positions

@@ -31,13 +31,28 @@ class TokParams(C.Structure):
         "n_bins", "cont_start", "disc_start", "vocab", "use_pos", "seq_len", "width", "ctx_rows")]
 
 
+class Dropout(C.Structure):
+    """neko_dropout (include/neko_b200.h): counter-based mask of one dropout site."""
+    _fields_ = [("seed", C.c_void_p), ("stream", C.c_uint32), ("thr16", C.c_uint32), ("scale", C.c_float), ("reserved", C.c_uint32)]
+
+    @classmethod
+    def make(cls, seed_tensor, stream: int, p: float):
+        """seed_tensor: int32/uint32 CUDA tensor of 2 words; p: drop probability (quantised to 16 bits)."""
+        thr = int(round(float(p) * 65536.0))
+        if seed_tensor is None or thr <= 0:
+            return cls(seed=None, stream=0, thr16=0, scale=1.0, reserved=0)
+        thr = min(thr, 65535)
+        return cls(seed=seed_tensor.data_ptr(), stream=int(stream), thr16=thr, scale=65536.0 / (65536.0 - thr), reserved=0)
+
+
 class GemmDesc(C.Structure):
     """neko_gemm_desc (include/neko_b200.h)."""
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32),
                 ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("flags", C.c_int32),
                 ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64),
                 ("C", C.c_void_p), ("ldc", C.c_int64), ("C2", C.c_void_p), ("ldc2", C.c_int64),
-                ("C3", C.c_void_p), ("ldc3", C.c_int64), ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_aux", C.c_int64)]
+                ("C3", C.c_void_p), ("ldc3", C.c_int64), ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_aux", C.c_int64),
+                ("drop", Dropout)]
 
 
 EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_DGELU_BF16, EPI_RESID_F32_BF16 = range(6)

@@ -12,6 +12,7 @@
 // transposed copies are ever built.  dh = 32 (24 heads x 32 at d=768) makes this op latency/exp-bound rather
 // than MMA-bound; it is <3% of the step FLOPs.
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace neko {
 
@@ -79,10 +80,12 @@ __device__ __forceinline__ void frag_b_kn(const Tile<DH>& t, int k0, int n0, int
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int DH>
+// DROP: attn_dropout (trajectory_gpt2.py:179) on the softmax weights: the row sum (normaliser) uses the undropped
+// probabilities, the P V product the masked and rescaled ones; mask element = (row (b*H + h)*S + query, column key).
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ first_valid,
                                                                bf16* __restrict__ out, bf16* __restrict__ out2, float* __restrict__ lse, int S,
-                                                               int S_valid, int H, float scale_log2, int out_f16) {
+                                                               int S_valid, int H, float scale_log2, int out_f16, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sQ{s0};
@@ -102,6 +105,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 #pragma unroll
   for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+  uint32_t rk_a = 0u, rk_b = 0u;
+  if (DROP) {
+    const uint32_t dkey = drop_key(drop);
+    rk_a = drop_rowkey(dkey, (uint32_t)((b * H + h) * S + row_a));
+    rk_b = drop_rowkey(dkey, (uint32_t)((b * H + h) * S + row_b));
+  }
 
   if (q_hi > lo && q_hi > q0) {
     const int j_begin = (lo / ATT_BLK) * ATT_BLK;
@@ -178,6 +187,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       }
       l_a = l_a * corr_a + sum_a;
       l_b = l_b * corr_b + sum_b;
+      if (DROP) {
+#pragma unroll
+        for (int n = 0; n < ATT_BLK / 8; ++n) {
+          const uint32_t pr = (uint32_t)((j0 + n * 8) >> 1) + q;
+          float m0, m1;
+          drop_pair(rk_a, pr, drop.thr16, drop.scale, m0, m1);
+          s[n][0] *= m0; s[n][1] *= m1;
+          drop_pair(rk_b, pr, drop.thr16, drop.scale, m0, m1);
+          s[n][2] *= m0; s[n][3] *= m1;
+        }
+      }
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) {
         o[n][0] *= corr_a; o[n][1] *= corr_a; o[n][2] *= corr_b; o[n][3] *= corr_b;
@@ -232,12 +252,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // backward.  dQ kernel first (it also produces delta[b,h,i] = sum_c dO[i,c] O[i,c] from the tiles it holds),
 // then the dK/dV kernel.  No atomics: each kernel owns its output rows and recomputes P.
 // ---------------------------------------------------------------------------------------------
-template <int DH>
+// With dropout:  O = (P o M) V  (M = mask * 1/(1-p)),  dP = (dO V^T) o M,  dS = P o (dP - delta),  delta = rowsum(dO o O).
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                                   const bf16* __restrict__ dout, const float* __restrict__ lse,
                                                                   float* __restrict__ delta, const int32_t* __restrict__ first_valid,
                                                                   bf16* __restrict__ dqkv, int S, int S_valid, int H, float scale,
-                                                                  float scale_log2, int out_f16) {
+                                                                  float scale_log2, int out_f16, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sQ{s0};
@@ -264,6 +285,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 #pragma unroll
   for (int n = 0; n < DH / 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
 
+  uint32_t rk_a = 0u, rk_b = 0u;
+  if (DROP) {
+    const uint32_t dkey = drop_key(drop);
+    rk_a = drop_rowkey(dkey, (uint32_t)((b * H + h) * S + row_a));
+    rk_b = drop_rowkey(dkey, (uint32_t)((b * H + h) * S + row_b));
+  }
   const bool live = (q_hi > lo) && (q_hi > q0);
   if (!live) {
     // delta of dead rows is never read with a non-zero P, but keep the buffer defined
@@ -345,6 +372,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
         const float p1 = (va && key + 1 >= lo && key + 1 <= row_a) ? exp2f(fmaf(s[n][1], scale_log2, -lse_a)) : 0.f;
         const float p2 = (vb && key >= lo && key <= row_b) ? exp2f(fmaf(s[n][2], scale_log2, -lse_bb)) : 0.f;
         const float p3 = (vb && key + 1 >= lo && key + 1 <= row_b) ? exp2f(fmaf(s[n][3], scale_log2, -lse_bb)) : 0.f;
+        if (DROP) {
+          const uint32_t pr = (uint32_t)((j0 + n * 8) >> 1) + q;
+          float m0, m1;
+          drop_pair(rk_a, pr, drop.thr16, drop.scale, m0, m1);
+          dp[n][0] *= m0; dp[n][1] *= m1;
+          drop_pair(rk_b, pr, drop.thr16, drop.scale, m0, m1);
+          dp[n][2] *= m0; dp[n][3] *= m1;
+        }
         s[n][0] = p0 * (dp[n][0] - del_a) * scale;
         s[n][1] = p1 * (dp[n][1] - del_a) * scale;
         s[n][2] = p2 * (dp[n][2] - del_b) * scale;
@@ -383,11 +418,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 }
 
 // dK, dV: one CTA owns 64 keys (4 warps x 16) of one head and sweeps the query tiles at or below it.
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                    const float* __restrict__ lse, const float* __restrict__ delta,
                                                                    const int32_t* __restrict__ first_valid, bf16* __restrict__ dqkv,
-                                                                   int S, int S_valid, int H, float scale, float scale_log2) {
+                                                                   int S, int S_valid, int H, float scale, float scale_log2, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sK{s0};
@@ -396,6 +431,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   auto sdO = [&](int bi) { return Tile<DH>{s0 + (4 + bi) * Tile<DH>::BYTES}; };
   float* s_lse = reinterpret_cast<float*>(smem_raw + 6 * Tile<DH>::BYTES);  // [2][64]
   float* s_delta = s_lse + 2 * ATT_BLK;                                      // [2][64]
+  uint32_t* s_rk = reinterpret_cast<uint32_t*>(s_delta + 2 * ATT_BLK);       // [2][64] dropout row keys of the query tile
 
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * ATT_BLK;
   const int d = H * DH;
@@ -416,6 +452,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
     dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
   }
   const bool live = (j0 + ATT_BLK > lo) && (j0 < S_valid);
+  const uint32_t dkey = DROP ? drop_key(drop) : 0u;
   if (live) {
     auto load_q_tile = [&](int bufi, int i0) {
       load_tile_async<DH>(sQ(bufi), base + h * DH, pitch, i0, S);
@@ -424,6 +461,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         const int i = i0 + threadIdx.x;
         s_lse[bufi * ATT_BLK + threadIdx.x] = (i < S) ? lse_b[i] * kLog2e : INFINITY;
         s_delta[bufi * ATT_BLK + threadIdx.x] = (i < S) ? delta_b[i] : 0.f;
+        if (DROP) s_rk[bufi * ATT_BLK + threadIdx.x] = drop_rowkey(dkey, (uint32_t)((b * H + h) * S + i));
       }
     };
     load_tile_async<DH>(sK, base + d + h * DH, pitch, j0, S);
@@ -483,11 +521,21 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         const float p10 = ok10 ? exp2f(fmaf(st[n][2], scale_log2, -l0)) : 0.f;
         const float p11 = ok11 ? exp2f(fmaf(st[n][3], scale_log2, -l1)) : 0.f;
         const float d0 = dlp[c0], d1 = dlp[c0 + 1];
-        dpt[n][0] = p00 * (dpt[n][0] - d0) * scale;
-        dpt[n][1] = p01 * (dpt[n][1] - d1) * scale;
-        dpt[n][2] = p10 * (dpt[n][2] - d0) * scale;
-        dpt[n][3] = p11 * (dpt[n][3] - d1) * scale;
-        st[n][0] = p00; st[n][1] = p01; st[n][2] = p10; st[n][3] = p11;
+        float m00 = 1.f, m01 = 1.f, m10 = 1.f, m11 = 1.f;
+        if (DROP) {  // element (query, key): bits of key pair (key >> 1), half-word key & 1
+          const uint32_t r0 = s_rk[buf * ATT_BLK + c0], r1 = s_rk[buf * ATT_BLK + c0 + 1];
+          const uint32_t sh = (uint32_t)(key_a & 1) << 4;   // key_b = key_a + 8 has the same parity
+          const uint32_t pa_ = (uint32_t)key_a >> 1, pb_ = (uint32_t)key_b >> 1;
+          m00 = ((drop_bits(r0, pa_) >> sh) & 0xffffu) >= drop.thr16 ? drop.scale : 0.f;
+          m01 = ((drop_bits(r1, pa_) >> sh) & 0xffffu) >= drop.thr16 ? drop.scale : 0.f;
+          m10 = ((drop_bits(r0, pb_) >> sh) & 0xffffu) >= drop.thr16 ? drop.scale : 0.f;
+          m11 = ((drop_bits(r1, pb_) >> sh) & 0xffffu) >= drop.thr16 ? drop.scale : 0.f;
+        }
+        dpt[n][0] = p00 * (dpt[n][0] * m00 - d0) * scale;
+        dpt[n][1] = p01 * (dpt[n][1] * m01 - d1) * scale;
+        dpt[n][2] = p10 * (dpt[n][2] * m10 - d0) * scale;
+        dpt[n][3] = p11 * (dpt[n][3] * m11 - d1) * scale;
+        st[n][0] = p00 * m00; st[n][1] = p01 * m01; st[n][2] = p10 * m10; st[n][3] = p11 * m11;
       }
       // dV += P^T dO ; dK += dS^T Q   (k index = query: tiles are [query][dh] -> transposed ldmatrix)
 #pragma unroll
@@ -538,34 +586,35 @@ static size_t fwd_smem() { return 5 * (size_t)Tile<DH>::BYTES; }
 template <int DH>
 static size_t dq_smem() { return 7 * (size_t)Tile<DH>::BYTES + ATT_BLK * sizeof(float); }
 template <int DH>
-static size_t dkv_smem() { return 6 * (size_t)Tile<DH>::BYTES + 4 * ATT_BLK * sizeof(float); }
+static size_t dkv_smem() { return 6 * (size_t)Tile<DH>::BYTES + 6 * ATT_BLK * sizeof(float); }
 
-template <int DH>
-static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int out_f16, cudaStream_t st) {
+template <int DH, bool DROP>
+static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int out_f16,
+                      DropCfg drop, cudaStream_t st) {
   const size_t smem = fwd_smem<DH>();
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_fwd)");
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(qkv, fv, out, out2, lse, S, S_valid, H, scale_log2, out_f16);
+  attn_fwd_kernel<DH, DROP><<<grid, ATT_THREADS, smem, st>>>(qkv, fv, out, out2, lse, S, S_valid, H, scale_log2, out_f16, drop);
   NEKO_LAUNCH_CHECK("attn_fwd_kernel");
   return NEKO_OK;
 }
 
-template <int DH>
+template <int DH, bool DROP>
 static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, const int32_t* fv, bf16* dqkv,
-                      int B, int S, int S_valid, int H, int out_f16, cudaStream_t st) {
+                      int B, int S, int S_valid, int H, int out_f16, DropCfg drop, cudaStream_t st) {
   const size_t s1 = dq_smem<DH>(), s2 = dkv_smem<DH>();
-  cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_bwd_dq)");
-  e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+  e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_bwd_dkv)");
   const float scale = 1.0f / sqrtf((float)DH);
   const float scale_log2 = 1.4426950408889634f * scale;
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, s1, st>>>(qkv, out, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, out_f16);
+  attn_bwd_dq_kernel<DH, DROP><<<grid, ATT_THREADS, s1, st>>>(qkv, out, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, out_f16, drop);
   NEKO_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<DH><<<grid, ATT_THREADS, s2, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2);
+  attn_bwd_dkv_kernel<DH, DROP><<<grid, ATT_THREADS, s2, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, drop);
   NEKO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return NEKO_OK;
 }
@@ -575,26 +624,32 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
 extern "C" {
 
 int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out, uint16_t* out2_bf16, float* lse, int B, int S,
-                       int S_valid, int H, int dh, int out_f16, void* stream) {
+                       int S_valid, int H, int dh, int out_f16, const neko_dropout* drop, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(qkv && first_valid && out && lse, "attention_fwd: null pointer");
   NEKO_REQUIRE(B > 0 && S > 0 && H > 0 && S_valid > 0 && S_valid <= S, "attention_fwd: bad sizes");
   NEKO_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention_fwd: misaligned");
+  NEKO_REQUIRE((long long)B * H * S < (1LL << 32), "attention_fwd: B*H*S exceeds the dropout row-id range");
   const bf16* x = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   bf16* o2 = reinterpret_cast<bf16*>(out2_bf16);
   cudaStream_t st = as_stream(stream);
+  const DropCfg dc = drop_cfg(drop);
+#define NEKO_ATT_FWD(DH_) (dc.seed ? launch_fwd<DH_, true>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, dc, st) \
+                                   : launch_fwd<DH_, false>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, dc, st))
   switch (dh) {
-    case 16: return launch_fwd<16>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
-    case 32: return launch_fwd<32>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
-    case 64: return launch_fwd<64>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
-    case 128: return launch_fwd<128>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, st);
+    case 16: return NEKO_ATT_FWD(16);
+    case 32: return NEKO_ATT_FWD(32);
+    case 64: return NEKO_ATT_FWD(64);
+    case 128: return NEKO_ATT_FWD(128);
     default: set_error("attention: head dim %d not supported (16, 32, 64, 128)", dh); return NEKO_EINVAL;
   }
+#undef NEKO_ATT_FWD
 }
 
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse, const int32_t* first_valid,
-                       uint16_t* dqkv, float* delta, int B, int S, int S_valid, int H, int dh, int out_f16, void* stream) {
+                       uint16_t* dqkv, float* delta, int B, int S, int S_valid, int H, int dh, int out_f16, const neko_dropout* drop,
+                       void* stream) {
   using namespace neko;
   NEKO_REQUIRE(qkv && out && dout && lse && first_valid && dqkv && delta, "attention_bwd: null pointer");
   NEKO_REQUIRE(B > 0 && S > 0 && H > 0 && S_valid > 0 && S_valid <= S, "attention_bwd: bad sizes");
@@ -605,13 +660,17 @@ int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t*
   const bf16* o = reinterpret_cast<const bf16*>(out);
   const bf16* g = reinterpret_cast<const bf16*>(dout);
   bf16* dx = reinterpret_cast<bf16*>(dqkv);
+  const DropCfg dc = drop_cfg(drop);
+#define NEKO_ATT_BWD(DH_) (dc.seed ? launch_bwd<DH_, true>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, dc, st) \
+                                   : launch_bwd<DH_, false>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, dc, st))
   switch (dh) {
-    case 16: return launch_bwd<16>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
-    case 32: return launch_bwd<32>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
-    case 64: return launch_bwd<64>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
-    case 128: return launch_bwd<128>(x, o, g, lse, delta, first_valid, dx, B, S, S_valid, H, out_f16, st);
+    case 16: return NEKO_ATT_BWD(16);
+    case 32: return NEKO_ATT_BWD(32);
+    case 64: return NEKO_ATT_BWD(64);
+    case 128: return NEKO_ATT_BWD(128);
     default: set_error("attention: head dim %d not supported (16, 32, 64, 128)", dh); return NEKO_EINVAL;
   }
+#undef NEKO_ATT_BWD
 }
 
 }  // extern "C"

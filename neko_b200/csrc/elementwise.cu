@@ -1,5 +1,7 @@
+#include <algorithm>
 // Memory-bound helpers around the GEMMs: dtype cast, bias-gradient column sums, row gather/scatter.
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace neko {
 
@@ -104,6 +106,34 @@ __global__ void __launch_bounds__(256) scatter_rows_add_kernel(const bf16* __res
   for (int i = lane; i < n; i += 32) d[i] += __bfloat162float(s[i]);
 }
 
+// ---- dropout on an fp32 [rows, cols] tensor in place (embd dropout and its backward), and the mask itself ----
+__global__ void __launch_bounds__(256) dropout_apply_kernel(float* __restrict__ x, long long ld, int rows, int cols, DropCfg drop) {
+  const uint32_t key = drop_key(drop);
+  const int pairs = (cols + 1) >> 1;
+  const long long total = (long long)rows * pairs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / pairs), pr = (int)(i - (long long)row * pairs);
+    float m0, m1;
+    drop_pair(drop_rowkey(key, (uint32_t)row), (uint32_t)pr, drop.thr16, drop.scale, m0, m1);
+    float* q = x + (long long)row * ld + 2 * pr;
+    q[0] *= m0;
+    if (2 * pr + 1 < cols) q[1] *= m1;
+  }
+}
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ keep, int rows, int cols, DropCfg drop) {
+  const uint32_t key = drop_key(drop);
+  const int pairs = (cols + 1) >> 1;
+  const long long total = (long long)rows * pairs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / pairs), pr = (int)(i - (long long)row * pairs);
+    float m0, m1;
+    drop_pair(drop_rowkey(key, (uint32_t)row), (uint32_t)pr, drop.thr16, 1.0f, m0, m1);
+    uint8_t* q = keep + (long long)row * cols + 2 * pr;
+    q[0] = m0 != 0.f;
+    if (2 * pr + 1 < cols) q[1] = m1 != 0.f;
+  }
+}
+
 }  // namespace neko
 
 extern "C" {
@@ -193,6 +223,29 @@ int neko_scatter_rows_add_f32(const uint16_t* src_bf16, int64_t ld_src, const in
   const long long blocks = ((long long)n_rows * 32 + 255) / 256;
   scatter_rows_add_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src_bf16), ld_src, rows, n_rows, n, dst, ld_dst);
   NEKO_LAUNCH_CHECK("scatter_rows_add_kernel");
+  return NEKO_OK;
+}
+
+int neko_dropout_apply(float* x, int64_t ld, int rows, int cols, const neko_dropout* drop, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(x && rows > 0 && cols > 0 && ld >= cols, "dropout_apply: bad arguments");
+  const DropCfg c = drop_cfg(drop);
+  if (!c.seed) return NEKO_OK;
+  const long long total = (long long)rows * ((cols + 1) / 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  dropout_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, ld, rows, cols, c);
+  NEKO_LAUNCH_CHECK("dropout_apply_kernel");
+  return NEKO_OK;
+}
+
+int neko_dropout_mask(uint8_t* keep, int rows, int cols, const neko_dropout* drop, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(keep && rows > 0 && cols > 0 && drop && drop->seed, "dropout_mask: bad arguments");
+  DropCfg c{drop->seed, drop->stream, drop->thr16, 1.0f};
+  const long long total = (long long)rows * ((cols + 1) / 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  dropout_mask_kernel<<<blocks, 256, 0, as_stream(stream)>>>(keep, rows, cols, c);
+  NEKO_LAUNCH_CHECK("dropout_mask_kernel");
   return NEKO_OK;
 }
 

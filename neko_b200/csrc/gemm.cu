@@ -24,6 +24,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace neko {
 
@@ -58,6 +59,7 @@ struct GemmParams {
   int pair;        // 1: cta_group::2 CTA pairs (256 x BN tile per pair)
   int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
   int kb_per_split;
+  DropCfg drop;    // RESID epilogues: C = aux + dropout(acc + bias)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -268,6 +270,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
     }
     default: {  // fp32 outputs
       float* c = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+      if (p.drop.seed && (p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16)) {
+        const uint32_t rk = drop_rowkey(drop_key(p.drop), (uint32_t)row);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float m0, m1;
+          drop_pair(rk, (uint32_t)((col0 >> 1) + i), p.drop.thr16, p.drop.scale, m0, m1);
+          f[2 * i] *= m0; f[2 * i + 1] *= m1;
+        }
+      }
       const float* add = nullptr;
       if (p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16)
         add = reinterpret_cast<const float*>(p.aux) + row * p.ld_aux + col0;
@@ -432,6 +443,15 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
       stage_and_store(s, mc, f, 0, p.accumulate || p.splits > 1, col0, row0);
       break;
     default: {  // NEKO_EPI_RESID_F32 / NEKO_EPI_RESID_F32_BF16
+      if (p.drop.seed) {  // resid_dropout on the branch output, before the residual add
+        const uint32_t rk = drop_rowkey(drop_key(p.drop), (uint32_t)row);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float m0, m1;
+          drop_pair(rk, (uint32_t)((col0 >> 1) + i), p.drop.thr16, p.drop.scale, m0, m1);
+          f[2 * i] *= m0; f[2 * i + 1] *= m1;
+        }
+      }
       if (in_rows) {
         const float* add = reinterpret_cast<const float*>(p.aux) + row * p.ld_aux + col0;
         if (fast) {
@@ -766,6 +786,8 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.epi = epilogue; p.accumulate = accumulate; p.flags = flags;
   p.C = C; p.ldc = ldc; p.C2 = C2; p.ldc2 = ldc2; p.C3 = C3; p.ldc3 = ldc3; p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.drop = drop_cfg(&gd->drop);
+  NEKO_REQUIRE(!p.drop.seed || epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_RESID_F32_BF16, "gemm: dropout is only defined for the residual epilogues");
   // tile shape, CTA pairing and split-K factor: minimise  waves x (main loop + epilogue)  in units of one k-block of a
   // 128 x 128 tile.  Per-k-block costs reflect the measured operand-traffic bound (profiles/): a single CTA moves
   // 32 KB (BN=128) or 48 KB (BN=256) per k-block, a CTA of a pair 24 KB / 32 KB for the same MMA work.  Split-K

@@ -5,6 +5,7 @@
 // the next dgrad/wgrad GEMM consumes.  HBM-bound; one warp per row, 128-bit accesses, row kept in
 // registers (d <= 2048).
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace neko {
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ rstd, float* __restrict__ dx_resid,
                                                             bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ dx_colsum, int N, int d,
-                                                            int rows_per_cta) {
+                                                            int rows_per_cta, DropCfg drop) {
   __shared__ float red[2][16][2 * LNB_ROWS];  // [parity][warp][s1 x4, s2 x4]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int c4 = threadIdx.x;            // this thread's float4 column group
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const bf16* __restri
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(N, row0 + rows_per_cta);
   const float inv_d = 1.0f / (float)d;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
   int parity = 0;
   for (int rb = row0; rb < row1; rb += LNB_ROWS, parity ^= 1) {
     float4 xv[LNB_ROWS], rv[LNB_ROWS];
@@ -137,6 +139,13 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const bf16* __restri
         o.w += rs[r] * (gy[r].w - m1 - xh[r].w * m2);
         const size_t off = (size_t)row * d;
         reinterpret_cast<float4*>(dx_resid + off)[c4] = o;
+        if (drop.seed) {  // gradient entering the dropped-out residual branch: mask * scale * dx
+          const uint32_t rk = drop_rowkey(dkey, (uint32_t)row);
+          float m0, m1, m2_, m3;
+          drop_pair(rk, 2u * c4, drop.thr16, drop.scale, m0, m1);
+          drop_pair(rk, 2u * c4 + 1u, drop.thr16, drop.scale, m2_, m3);
+          o.x *= m0; o.y *= m1; o.z *= m2_; o.w *= m3;
+        }
         if (dx_bf16) reinterpret_cast<uint2*>(dx_bf16 + off)[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
       }
@@ -175,7 +184,8 @@ int neko_layernorm_fwd(const float* x, const float* gamma, const float* beta, ui
 }
 
 int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gamma, const float* mean, const float* rstd,
-                       float* dx_resid, uint16_t* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int N, int d, void* stream) {
+                       float* dx_resid, uint16_t* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int N, int d,
+                       const neko_dropout* branch_drop, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(dy_bf16 && x && gamma && mean && rstd && dx_resid && dgamma && dbeta, "layernorm_bwd: null pointer");
   NEKO_REQUIRE(N > 0 && d > 0 && d % 4 == 0 && d <= LN_MAX_D, "layernorm_bwd: need d %% 4 == 0 and d <= %d (got %d)", LN_MAX_D, d);
@@ -186,7 +196,8 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
   rows_per_cta = ((rows_per_cta + LNB_ROWS - 1) / LNB_ROWS) * LNB_ROWS;
   ctas = (N + rows_per_cta - 1) / rows_per_cta;
   layernorm_bwd_kernel<<<ctas, threads, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid,
-                                                                reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dx_colsum, N, d, rows_per_cta);
+                                                                reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dx_colsum, N, d, rows_per_cta,
+                                                                drop_cfg(branch_drop));
   NEKO_LAUNCH_CHECK("layernorm_bwd_kernel");
   return NEKO_OK;
 }

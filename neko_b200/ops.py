@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_RESID_F32_BF16,  # noqa: F401
-                   GemmDesc, SampleDesc, TokParams, _p, check, load, stream_ptr)
+                   Dropout, GemmDesc, SampleDesc, TokParams, _p, check, load, stream_ptr)
 
 
 _16BIT = (torch.bfloat16, torch.float16)
@@ -37,7 +37,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, out3: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, accumulate: bool = False,
          M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
-         out_dtype: torch.dtype = torch.bfloat16):
+         out_dtype: torch.dtype = torch.bfloat16, drop: Optional[Dropout] = None):
     """C[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: 16-bit [M,K] (a_mn=False) or [K,M] (a_mn=True); b: same format, [N,K] or [K,N]; rows may be strided
@@ -65,6 +65,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                   C2=_ptr(out2), ldc2=out2.stride(0) if out2 is not None else 0,
                   C3=_ptr(out3), ldc3=out3.stride(0) if out3 is not None else 0,
                   bias=_ptr(bias), aux=_ptr(aux), ld_aux=aux.stride(0) if aux is not None else 0)
+    if drop is not None:   # RESID epilogues: C = aux + dropout(acc + bias)
+        gd.drop = drop
     if GEMM_TIMING is not None:  # bench.py: CUDA events around every tensor-core launch (roofline.achieved)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -96,18 +98,39 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf16=None, dx_colsum=None):
+def _dref(drop):
+    return C.byref(drop) if drop is not None else None
+
+
+def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf16=None, dx_colsum=None, branch_drop=None):
     N, d = x.shape
     check(load().neko_layernorm_bwd(_p(dy_bf16), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_resid), _p(dx_bf16),
-                                    _p(dgamma), _p(dbeta), _p(dx_colsum), C.c_int(N), C.c_int(d), stream_ptr()),
+                                    _p(dgamma), _p(dbeta), _p(dx_colsum), C.c_int(N), C.c_int(d), _dref(branch_drop), stream_ptr()),
           "neko_layernorm_bwd")
+
+
+def dropout_apply(x: torch.Tensor, drop: Optional[Dropout]):
+    """x fp32 [rows, cols] *= mask * scale, in place (embd dropout, trajectory_gpt2.py:707, and its backward)."""
+    if drop is None or not drop.thr16:
+        return x
+    rows, cols = x.shape
+    check(load().neko_dropout_apply(_p(x), C.c_int64(x.stride(0)), C.c_int(rows), C.c_int(cols), C.byref(drop), stream_ptr()),
+          "neko_dropout_apply")
+    return x
+
+
+def dropout_mask(rows: int, cols: int, drop: Dropout, device) -> torch.Tensor:
+    """The keep mask (uint8 [rows, cols]) the kernels generate for this site: tests replay a step with it."""
+    keep = torch.empty(rows, cols, dtype=torch.uint8, device=device)
+    check(load().neko_dropout_mask(_p(keep), C.c_int(rows), C.c_int(cols), C.byref(drop), stream_ptr()), "neko_dropout_mask")
+    return keep
 
 
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
 def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid: Optional[int] = None, out=None, lse=None,
-                  out_dtype: torch.dtype = torch.bfloat16, out2=None):
+                  out_dtype: torch.dtype = torch.bfloat16, out2=None, drop=None):
     B, S, three_d = qkv.shape
     d = three_d // 3
     dh = d // H
@@ -117,11 +140,11 @@ def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid:
         lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
     check(load().neko_attention_fwd(_p(qkv), _p(first_valid), _p(out), _p(out2), _p(lse), C.c_int(B), C.c_int(S),
                                     C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh),
-                                    C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_attention_fwd")
+                                    C.c_int(int(out.dtype == torch.float16)), _dref(drop), stream_ptr()), "neko_attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[int] = None, dqkv=None, delta=None):
+def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[int] = None, dqkv=None, delta=None, drop=None):
     B, S, three_d = qkv.shape
     dh = three_d // 3 // H
     if dqkv is None:
@@ -130,7 +153,7 @@ def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[in
         delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
     check(load().neko_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(first_valid), _p(dqkv), _p(delta), C.c_int(B),
                                     C.c_int(S), C.c_int(S if S_valid is None else S_valid), C.c_int(H), C.c_int(dh),
-                                    C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_attention_bwd")
+                                    C.c_int(int(out.dtype == torch.float16)), _dref(drop), stream_ptr()), "neko_attention_bwd")
     return dqkv
 
 

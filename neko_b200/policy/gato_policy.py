@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, ops
-from .._lib import TokParams, _p, check, load, stream_ptr
+from .._lib import Dropout, TokParams, _p, check, load, stream_ptr
 from .embeddings import ImageEmbedding, _AffineParams, _EmbeddingParams, _LinearParams
 from .input_tokenizers import ContinuousTokenizer
 from .packing import BatchPlan, Stager, build_plan
@@ -50,7 +50,7 @@ class _Conv1D(nn.Module):
 
 
 class _Attention(nn.Module):
-    def __init__(self, nx: int, n_ctx: int):
+    def __init__(self, nx: int, n_ctx: int, attn_pdrop: float = 0.0, resid_pdrop: float = 0.0):
         super().__init__()
         # buffers kept for state_dict compatibility (trajectory_gpt2.py:127-130); the kernels derive the
         # causal structure arithmetically
@@ -58,13 +58,16 @@ class _Attention(nn.Module):
         self.register_buffer("masked_bias", torch.tensor(-1e4))
         self.c_attn = _Conv1D(3 * nx, nx)
         self.c_proj = _Conv1D(nx, nx)
+        self.attn_dropout = nn.Dropout(attn_pdrop)      # trajectory_gpt2.py:142-143 (p read by the kernels)
+        self.resid_dropout = nn.Dropout(resid_pdrop)
 
 
 class _MLP(nn.Module):
-    def __init__(self, n_state: int, nx: int, gate: bool):
+    def __init__(self, n_state: int, nx: int, gate: bool, resid_pdrop: float = 0.0):
         super().__init__()
         self.c_fc = _Conv1D(n_state, nx)
         self.c_proj = _Conv1D(nx, n_state)
+        self.dropout = nn.Dropout(resid_pdrop)          # trajectory_gpt2.py:271,278
         if gate:
             self.gated_layer = _LinearParams(nx, n_state)
             nn.init.normal_(self.gated_layer.weight, std=0.02)
@@ -74,12 +77,12 @@ class _MLP(nn.Module):
 
 
 class _Block(nn.Module):
-    def __init__(self, nx: int, n_ctx: int, gate: bool):
+    def __init__(self, nx: int, n_ctx: int, gate: bool, attn_pdrop: float = 0.0, resid_pdrop: float = 0.0):
         super().__init__()
         self.ln_1 = _AffineParams(nx)
-        self.attn = _Attention(nx, n_ctx)
+        self.attn = _Attention(nx, n_ctx, attn_pdrop, resid_pdrop)
         self.ln_2 = _AffineParams(nx)
-        self.mlp = _MLP(4 * nx, nx, gate)
+        self.mlp = _MLP(4 * nx, nx, gate, resid_pdrop)
 
 
 class _GPT2Config:
@@ -95,7 +98,8 @@ class GPT2Model(nn.Module):
         self.config = config
         self.wte = _EmbeddingParams(config.vocab_size, config.n_embd, std=0.02)  # never used (wpe/wte removed, :540,698-701)
         self.drop = nn.Dropout(config.embd_pdrop)
-        self.h = nn.ModuleList([_Block(config.n_embd, config.n_ctx, config.gate) for _ in range(config.n_layer)])
+        self.h = nn.ModuleList([_Block(config.n_embd, config.n_ctx, config.gate, config.attn_pdrop, config.resid_pdrop)
+                                for _ in range(config.n_layer)])
         self.ln_f = _AffineParams(config.n_embd)
 
     def forward(self, inputs_embeds=None, attention_mask=None, **kw):
@@ -262,6 +266,7 @@ class GatoPolicy(nn.Module):
         self._graph_pool = None
         self._gscale_buf = torch.ones((), dtype=torch.float32, device=dev)
         self.launches = 0
+        self._drop_gen = None
         self._build_arena()
 
     # ------------------------------------------------------------------------------------------
@@ -494,8 +499,10 @@ class GatoPolicy(nn.Module):
                 rb[off:off + T * n_h * n_w] = np.tile(np.repeat(hp.numpy(), n_w), T)
                 cb[off:off + T * n_h * n_w] = np.tile(np.tile(wp.numpy(), n_h), T)
             st.row_bins, st.col_bins = rb, cb
-        descs, fv, iv, first_valid, loss_rows, h2d = self._stager.upload(plan)
+        descs, fv, iv, first_valid, loss_rows, h2d, hdr = self._stager.upload(plan, self._next_drop_seed())
         st.descs, st.fvals, st.ivals, st.first_valid, st.loss_rows = descs, fv, iv, first_valid, loss_rows
+        st.drop_seed = hdr[:2]
+        self._last_drop = (st.drop_seed, plan.B, plan.width)
         st.h2d_bytes = h2d
         return st
 
@@ -613,23 +620,72 @@ class GatoPolicy(nn.Module):
         st.tmask = self._buf("tmask", (N,), torch.float32)
         st.mask = self._buf("mask", (N,), torch.float32)
         st.x0 = self._buf("x.0" if keep else "x.a", (N, d), torch.float32)
-        prm = self._tok_params(plan)
-        st.tok_params = prm
+        st.tok_params = self._tok_params(plan)
+        self._launch_tokenize(st)
+
+    def _launch_tokenize(self, st: _State):
+        """The tokenise + embed + interleave + pad kernel alone (bench.py times it against the HBM roofline)."""
+        plan, d, prm = st.plan, self.embed_dim, st.tok_params
         check(load().neko_tokenize_embed_fwd(_p(st.descs), C.c_int(plan.B), C.c_int(d), C.byref(prm), _p(st.fvals), _p(st.ivals),
                                              _p(st.patch_emb), _p(self.embed_token.weight), _p(self.pos_embed_observation.weight),
                                              _p(self.separator_token), _p(st.tokens), _p(st.tmask), _p(st.mask), _p(st.x0), _p(None),
                                              stream_ptr()), "neko_tokenize_embed_fwd")
         self.launches += 1
 
-    def _check_dropout(self):
-        if self.training and (self.dropout > 0 or self.transformer.drop.p > 0):
-            raise NotImplementedError(
-                "dropout is not implemented in the CUDA path yet: construct with dropout=0 and set "
-                "model.transformer.drop.p = 0 (embd_pdrop is 0.1 in the reference whatever --dropout says, SURVEY quirk 8)")
+    # -- dropout ------------------------------------------------------------------------------------
+    # Sites (include/neko_b200.h neko_dropout.stream): 0 embeddings (transformer.drop, p = 0.1 whatever --dropout says,
+    # SURVEY quirk 8), 4*layer+1 attention weights, 4*layer+2 attention residual branch, 4*layer+3 MLP residual branch.
+    # Masks are counter based: the two seed words travel with the batch upload, kernels regenerate the mask in backward.
+    def _dropout_ps(self):
+        if not self.training:
+            return None
+        ps = [float(self.transformer.drop.p)]
+        for blk in self.transformer.h:
+            ps += [float(blk.attn.attn_dropout.p), float(blk.attn.resid_dropout.p), float(blk.mlp.dropout.p)]
+        return tuple(ps) if any(ps) else None
+
+    def _next_drop_seed(self):
+        if self._dropout_ps() is None:
+            return None
+        if self._drop_gen is None:   # own generator: the global CPU stream keeps feeding the patch-position draws only
+            self._drop_gen = torch.Generator()
+            self._drop_gen.manual_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        return torch.randint(0, 2 ** 31 - 1, (2,), generator=self._drop_gen, dtype=torch.int32).numpy()
+
+    def dropout_multipliers(self):
+        """The multipliers (mask / (1 - p_eff)) the kernels applied in the most recent train-mode forward, keyed like
+        ``oracle.gato_oracle.decoder(drop=...)``: lets a test (or a debugging session) replay the step in a reference."""
+        ps = self._dropout_ps()
+        if ps is None or getattr(self, "_last_drop", None) is None:
+            return {}
+        seed, B, W = self._last_drop
+        d, H = self.embed_dim, self.heads
+
+        def mult(stream, p, rows, cols):
+            dr = Dropout.make(seed, stream, p)
+            return ops.dropout_mask(rows, cols, dr, self.device).to(torch.float32) * dr.scale
+
+        out = {}
+        if ps[0] > 0:
+            out["embd"] = mult(0, ps[0], B * W, d).view(B, W, d)
+        for i in range(self.layers):
+            pa, pr, pm = ps[1 + 3 * i:4 + 3 * i]
+            if pa > 0:
+                out[("attn", i)] = mult(4 * i + 1, pa, B * H * W, W).view(B, H, W, W)
+            if pr > 0:
+                out[("resid_attn", i)] = mult(4 * i + 2, pr, B * W, d).view(B, W, d)
+            if pm > 0:
+                out[("resid_mlp", i)] = mult(4 * i + 3, pm, B * W, d).view(B, W, d)
+        return out
+
+    def _drop_site(self, st: _State, stream: int, p: float):
+        seed = getattr(st, "drop_seed", None)
+        if not self.training or p <= 0.0 or seed is None:
+            return None
+        return Dropout.make(seed, stream, p)
 
     def _decoder(self, st: _State, x: torch.Tensor, B: int, W: int, S_valid: int, first_valid: torch.Tensor, keep: bool):
         """L pre-LN blocks + ln_f (trajectory_gpt2.py:322-358, 779).  x fp32 [N,d] -> hf bf16 [N,d]."""
-        self._check_dropout()
         if self.transformer.config.gate:
             raise NotImplementedError("activation_fn='geglu' (SURVEY.md section 8(f).4) is not implemented in the CUDA path")
         d, H = self.embed_dim, self.heads
@@ -646,6 +702,10 @@ class GatoPolicy(nn.Module):
                 return t, (t if keep else None)
             return self._buf(name, shape, fdt), self._buf(name + ".b" + tag, shape, torch.bfloat16)
 
+        d0 = self._drop_site(st, 0, self.transformer.drop.p)
+        if d0 is not None:                      # hidden_states = self.drop(inputs_embeds), trajectory_gpt2.py:707
+            ops.dropout_apply(x, d0)
+            self.launches += 1
         for i, blk in enumerate(self.transformer.h):
             tag = f".{i}" if keep else ""
             pre = f"transformer.h.{i}."
@@ -658,10 +718,10 @@ class GatoPolicy(nn.Module):
             att, att_b = pair("att", tag, (N, d))
             lse = self._buf("lse" + tag, (B, H, W), torch.float32)
             ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse,
-                              out2=att_b.view(B, W, d) if dual else None)
+                              out2=att_b.view(B, W, d) if dual else None, drop=self._drop_site(st, 4 * i + 1, blk.attn.attn_dropout.p))
             x1 = self._buf(f"x.{2 * i + 1}" if keep else "x.b", (N, d), torch.float32)
             ops.gemm(att, self._wview(pre + "attn.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x1, aux=x,
-                     bias=blk.attn.c_proj.bias)
+                     bias=blk.attn.c_proj.bias, drop=self._drop_site(st, 4 * i + 2, blk.attn.resid_dropout.p))
             ln2, ln2_b = pair("ln2", tag, (N, d))
             m2 = self._buf("m2" + tag, (N,), torch.float32)
             r2 = self._buf("r2" + tag, (N,), torch.float32)
@@ -672,7 +732,7 @@ class GatoPolicy(nn.Module):
                      out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias)
             x2 = self._buf(f"x.{2 * i + 2}" if keep else "x.a", (N, d), torch.float32)
             ops.gemm(fact, self._wview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
-                     bias=blk.mlp.c_proj.bias)
+                     bias=blk.mlp.c_proj.bias, drop=self._drop_site(st, 4 * i + 3, blk.mlp.dropout.p))
             self.launches += 7
             if keep:
                 acts.append((x, ln1_b, m1, r1, qkv, att_b, lse, x1, ln2_b, m2, r2, fpre, fact_b))
@@ -711,6 +771,8 @@ class GatoPolicy(nn.Module):
             else:  # first valid key per sample; right padding is never visible to a valid (causal) query
                 fv = (mask.to(self.device).cumsum(1) == 0).sum(1).to(torch.int32)
             st = _State()
+            seed = self._next_drop_seed()
+            st.drop_seed = torch.from_numpy(seed).to(self.device) if seed is not None else None
             return self._decoder(st, x, B, S, S, fv, keep=False)
 
     # -- CUDA graphs -------------------------------------------------------------------------------------
@@ -721,7 +783,7 @@ class GatoPolicy(nn.Module):
         p = st.plan
         return (p.B, p.seq_len, p.width, p.descs.tobytes(), tuple((g.height, g.width, g.is_u8, g.n_frames) for g in p.image_groups),
                 len(p.precomputed_patch), st.compute_loss, st.need_grad, self.training, self.materialize_logits, self.head_mode,
-                self.fwd_dtype, st.row_bins is not None)
+                self.fwd_dtype, st.row_bins is not None, self._dropout_ps())
 
     def _engine_forward(self, st: _State):
         if not self.use_cuda_graphs:
@@ -907,8 +969,12 @@ class GatoPolicy(nn.Module):
         last = f"transformer.h.{self.layers - 1}."
         # the bias gradient of a residual-feeding Conv1D is the column sum of the residual gradient: LN backward
         # emits it for free (mlp.c_proj.bias of the block below, attn.c_proj.bias of the same block)
+        # With dropout the bf16 copy (and the column sum) carry mask * scale * dx: the gradient entering the dropped-out
+        # residual branch below this LN (branch_drop); the fp32 dx keeps the undropped residual-path gradient.
+        D = lambda s, pp: self._drop_site(st, s, pp)  # noqa: E731
+        hL = self.transformer.h[self.layers - 1]
         ops.layernorm_bwd(dhf, st.x_last, lnf.weight, st.mf, st.rf, dx, G("transformer.ln_f.weight"), G("transformer.ln_f.bias"), dxb,
-                          dx_colsum=G(last + "mlp.c_proj.bias"))
+                          dx_colsum=G(last + "mlp.c_proj.bias"), branch_drop=D(4 * (self.layers - 1) + 3, hL.mlp.dropout.p))
         self.launches += 2
         self._notify("transformer.ln_f.weight", "transformer.ln_f.bias")
 
@@ -928,7 +994,7 @@ class GatoPolicy(nn.Module):
             dln = self._buf("dln", (N, d), torch.bfloat16)
             ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_BF16, out=dln)
             ops.layernorm_bwd(dln, x1, blk.ln_2.weight, m2, r2, dx, G(pre + "ln_2.weight"), G(pre + "ln_2.bias"), dxb,
-                              dx_colsum=G(pre + "attn.c_proj.bias"))
+                              dx_colsum=G(pre + "attn.c_proj.bias"), branch_drop=D(4 * i + 2, blk.attn.resid_dropout.p))
             # attention: x1 = x0 + attn(ln1 @ Wqkv + b) @ Wproj + b
             ops.gemm(att, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "attn.c_proj.weight"), accumulate=acc,
                      M=d, N=d, K=N)
@@ -937,17 +1003,22 @@ class GatoPolicy(nn.Module):
             dqkv = self._buf("dqkv", (N, 3 * d), torch.bfloat16)
             delta = self._buf("delta", (B, H, W), torch.float32)
             ops.attention_bwd(qkv.view(B, W, 3 * d), att.view(B, W, d), datt.view(B, W, d), lse, st.first_valid, H, plan.seq_len,
-                              dqkv.view(B, W, 3 * d), delta)
+                              dqkv.view(B, W, 3 * d), delta, drop=D(4 * i + 1, blk.attn.attn_dropout.p))
             ops.gemm(ln1, dqkv, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "attn.c_attn.weight"), accumulate=acc,
                      M=d, N=3 * d, K=N)
             ops.colsum(dqkv, G(pre + "attn.c_attn.bias"), accumulate=True)
             ops.gemm(dqkv, Wb(pre + "attn.c_attn.weight"), epilogue=ops.EPI_BF16, out=dln)
             ops.layernorm_bwd(dln, x0, blk.ln_1.weight, m1, r1, dx, G(pre + "ln_1.weight"), G(pre + "ln_1.bias"), dxb,
-                              dx_colsum=G(f"transformer.h.{i - 1}.mlp.c_proj.bias") if i > 0 else None)
+                              dx_colsum=G(f"transformer.h.{i - 1}.mlp.c_proj.bias") if i > 0 else None,
+                              branch_drop=D(4 * (i - 1) + 3, self.transformer.h[i - 1].mlp.dropout.p) if i > 0 else None)
             self.launches += 14
             self._notify(pre + "mlp.c_proj.weight", pre + "ln_1.bias")
 
         # ---- embeddings ---------------------------------------------------------------------------------------
+        d0 = D(0, self.transformer.drop.p)
+        if d0 is not None:      # backward of the embedding dropout: same mask on the gradient
+            ops.dropout_apply(dx, d0)
+            self.launches += 1
         dpe = None
         if plan.n_patch_rows and getattr(st, "img_groups", None):
             dpe = self._buf("d_patch_emb", (plan.n_patch_rows, d), torch.float32)

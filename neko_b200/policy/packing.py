@@ -218,9 +218,11 @@ class Stager:
         self._next = (self._next + 1) % self.RING
         self._event.synchronize()
 
-    def upload(self, plan: BatchPlan):
-        """Returns device views: descs(u8), fvals(f32), ivals(i32), first_valid(i32), loss_rows(i32) and the
-        number of host->device bytes moved."""
+    HEADER = 256  # bytes at offset 0 of the staging buffer: per-step scalars (dropout seed words)
+
+    def upload(self, plan: BatchPlan, header: Optional[np.ndarray] = None):
+        """Returns device views: descs(u8), fvals(f32), ivals(i32), first_valid(i32), loss_rows(i32), the
+        number of host->device bytes moved and the int32 view of the header region."""
         def al(n):
             return (n + 255) // 256 * 256
         host_f = all(not t.is_cuda for t in plan.fvals)
@@ -228,7 +230,7 @@ class Stager:
         # every region always exists in the (pointer-stable) device buffer, whatever the source of the values: CUDA
         # graphs captured on this batch shape keep reading the same addresses
         sizes = [plan.descs.nbytes, plan.n_f * 4, plan.n_i * 4, plan.first_valid.nbytes, plan.loss_rows.nbytes]
-        offs = np.cumsum([0] + [al(s) for s in sizes])
+        offs = np.cumsum([self.HEADER] + [al(s) for s in sizes])
         total = int(offs[-1])
         self._ensure(total)
         pin = self._pinned
@@ -238,6 +240,10 @@ class Stager:
             return dev[offs[i]:offs[i] + sizes[i]].view(dtype)
 
         h2d = 0
+        hdr = np.zeros(self.HEADER // 4, dtype=np.int32)
+        if header is not None:
+            hdr[:header.size] = header.view(np.int32)
+        pin[:self.HEADER] = torch.from_numpy(hdr.view(np.uint8))
         # descriptors + first_valid + loss rows (+ host-resident values): one pinned -> device copy each contiguous run
         pin[offs[0]:offs[0] + sizes[0]] = torch.from_numpy(plan.descs)
         if host_f and plan.n_f:
@@ -251,6 +257,8 @@ class Stager:
             dev[:total].copy_(pin[:total], non_blocking=True)
             h2d = total
         else:
+            dev[:self.HEADER].copy_(pin[:self.HEADER], non_blocking=True)
+            h2d += self.HEADER
             for i in range(5):
                 if sizes[i] and not ((i == 1 and not host_f) or (i == 2 and not host_i)):
                     dev[offs[i]:offs[i] + sizes[i]].copy_(pin[offs[i]:offs[i] + sizes[i]], non_blocking=True)
@@ -264,4 +272,4 @@ class Stager:
         descs = dev[offs[0]:offs[0] + sizes[0]]
         fv = view(1, torch.float32)
         iv = view(2, torch.int32)
-        return descs, fv, iv, view(3, torch.int32), view(4, torch.int32), h2d
+        return descs, fv, iv, view(3, torch.int32), view(4, torch.int32), h2d, dev[:self.HEADER].view(torch.int32)

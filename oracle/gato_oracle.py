@@ -375,11 +375,19 @@ def embed_and_interleave(inputs: Sequence[dict], tb: TokenizedBatch, w: Dict[str
     return out
 
 
-def decoder(x: torch.Tensor, token_masks: torch.Tensor, w: Dict[str, torch.Tensor], cfg: GatoConfig
-            ) -> torch.Tensor:
-    """GPT2Model.forward on ``inputs_embeds`` with all dropouts at 0
-    (trajectory_gpt2.py:663-679 mask, :322-358 block, :163-188 attention, :273-278 MLP, :779 ln_f)."""
+def decoder(x: torch.Tensor, token_masks: torch.Tensor, w: Dict[str, torch.Tensor], cfg: GatoConfig,
+            drop: Optional[Dict] = None) -> torch.Tensor:
+    """GPT2Model.forward on ``inputs_embeds``
+    (trajectory_gpt2.py:663-679 mask, :322-358 block, :163-188 attention, :273-278 MLP, :779 ln_f).
+
+    ``drop`` = None: all dropouts off.  Otherwise a dict of explicit multipliers (mask / (1 - p)) for the reference's four
+    dropout sites, so a train-mode step can be replayed deterministically: ``"embd"`` [B,S,d] (self.drop, :707),
+    ``("attn", i)`` [B,H,S,S] (attn_dropout on the softmax weights, :179), ``("resid_attn", i)`` [B,S,d] (resid_dropout
+    after attn.c_proj, :254), ``("resid_mlp", i)`` [B,S,d] (mlp.dropout after mlp.c_proj, :278)."""
+    drop = drop or {}
     B, S, d = x.shape
+    if "embd" in drop:
+        x = x * drop["embd"]
     H = cfg.heads
     dh = d // H
     pad_bias = ((1.0 - token_masks.to(torch.float32)) * -10000.0)[:, None, None, :]
@@ -397,14 +405,20 @@ def decoder(x: torch.Tensor, token_masks: torch.Tensor, w: Dict[str, torch.Tenso
         s = torch.where(causal, s, neg)
         s = s + pad_bias
         pr = torch.softmax(s, dim=-1)
+        if ("attn", i) in drop:
+            pr = pr * drop[("attn", i)]
         o = torch.matmul(pr, v).permute(0, 2, 1, 3).reshape(B, S, d)
         o = torch.addmm(w[p + "attn.c_proj.bias"], o.reshape(-1, d), w[p + "attn.c_proj.weight"]).reshape(B, S, d)
+        if ("resid_attn", i) in drop:
+            o = o * drop[("resid_attn", i)]
         x = o + x
         m = F.layer_norm(x, (d,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], cfg.layer_norm_eps)
         hmid = gelu_erf(torch.addmm(w[p + "mlp.c_fc.bias"], m.reshape(-1, d), w[p + "mlp.c_fc.weight"]))
         if cfg.activation_fn == "geglu":
             hmid = hmid * F.linear(m.reshape(-1, d), w[p + "mlp.gated_layer.weight"], w[p + "mlp.gated_layer.bias"])
         m = torch.addmm(w[p + "mlp.c_proj.bias"], hmid, w[p + "mlp.c_proj.weight"]).reshape(B, S, d)
+        if ("resid_mlp", i) in drop:
+            m = m * drop[("resid_mlp", i)]
         x = x + m
     return F.layer_norm(x, (d,), w["transformer.ln_f.weight"], w["transformer.ln_f.bias"], cfg.layer_norm_eps)
 
@@ -431,14 +445,15 @@ class OracleOutput:
 
 
 def forward(w: Dict[str, torch.Tensor], inputs: Sequence[dict], cfg: GatoConfig, compute_loss: bool = True,
-            training: bool = False, patch_pos: Optional[List] = None) -> OracleOutput:
-    """GatoPolicy.forward(inputs, compute_loss) (gato_policy.py:156-192) with dropout off."""
+            training: bool = False, patch_pos: Optional[List] = None, drop: Optional[Dict] = None) -> OracleOutput:
+    """GatoPolicy.forward(inputs, compute_loss) (gato_policy.py:156-192); dropout off unless explicit multipliers are
+    given in ``drop`` (see ``decoder``)."""
     tb = tokenize(inputs, cfg)
     emb = embed_and_interleave(inputs, tb, w, cfg, training, patch_pos)
     tokens = torch.from_numpy(tb.tokens)
     tmask = torch.from_numpy(tb.target_masks)
     mask = torch.from_numpy(tb.token_masks)
-    hid = decoder(emb, mask, w, cfg)
+    hid = decoder(emb, mask, w, cfg, drop)
     logits = F.linear(hid, w["predict_token.weight"])
     loss = masked_cross_entropy(logits, tokens, tmask, mask) if compute_loss else None
     return OracleOutput(emb, tokens, tmask, mask, hid, logits, loss)

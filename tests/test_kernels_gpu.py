@@ -386,3 +386,92 @@ def test_patch_resblock(ops, groups, u8):
                                            _p(grads[0]), _p(grads[1]), _p(grads[2]), _p(grads[3]), _p(grads[4]), _p(grads[5]),
                                            stream_ptr()), "bwd")
     assert ((grads[0] - 2 * params[0].grad).norm() / params[0].grad.norm()).item() < 4e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# dropout primitives
+# ---------------------------------------------------------------------------------------------------
+def _seed(a, b):
+    return torch.tensor([a, b], dtype=torch.int32, device="cuda")
+
+
+def test_dropout_mask_apply_and_statistics(ops):
+    from neko_b200._lib import Dropout
+    s = _seed(123, 456)
+    for p in (0.1, 0.5):
+        dr = Dropout.make(s, 7, p)
+        keep = ops.dropout_mask(1000, 777, dr, "cuda")
+        rate = keep.float().mean().item()
+        assert abs(rate - (1 - p)) < 5e-3, rate
+        # columns / rows are not correlated with each other
+        assert abs(keep[:, ::2].float().mean().item() - keep[:, 1::2].float().mean().item()) < 1e-2
+        assert (keep[:-1] == keep[1:]).float().mean().item() < (p * p + (1 - p) * (1 - p)) + 1e-2
+        x = _rand((1000, 777), 5)
+        y = x.clone()
+        ops.dropout_apply(y, dr)
+        assert torch.equal(y, x * keep.float() * dr.scale)
+        # another stream / another seed -> another mask; same (seed, stream) -> same mask
+        assert not torch.equal(keep, ops.dropout_mask(1000, 777, Dropout.make(s, 8, p), "cuda"))
+        assert not torch.equal(keep, ops.dropout_mask(1000, 777, Dropout.make(_seed(124, 456), 7, p), "cuda"))
+        assert torch.equal(keep, ops.dropout_mask(1000, 777, Dropout.make(s, 7, p), "cuda"))
+    assert Dropout.make(s, 1, 0.0).thr16 == 0
+
+
+def test_gemm_residual_dropout_and_layernorm_bwd_branch_mask(ops):
+    from neko_b200._lib import Dropout
+    M, N, K = 520, 768, 256
+    dr = Dropout.make(_seed(9, 10), 6, 0.25)
+    a = _rand((M, K), 1, 1.0, torch.float16)
+    b = _rand((K, N), 2, 0.05, torch.float16)
+    bias = _rand((N,), 3)
+    res = _rand((M, N), 4)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, b_mn=True, epilogue=ops.EPI_RESID_F32, out=out, aux=res, bias=bias, drop=dr)
+    mult = ops.dropout_mask(M, N, dr, "cuda").float() * dr.scale
+    ref = res + (a.float() @ b.float() + bias) * mult
+    assert (out - ref).abs().max().item() < 2e-3
+    # LN backward: dx_bf16 / dx_colsum carry mask * scale * dx, the fp32 residual gradient stays unmasked
+    d = N
+    x = _rand((M, d), 5)
+    gamma = 1 + _rand((d,), 6, 0.1)
+    dy = _rand((M, d), 7, 1.0, torch.bfloat16)
+    dx0 = _rand((M, d), 8)
+    mean = x.mean(1)
+    rstd = (x.var(1, unbiased=False) + 1e-5).rsqrt()
+    dxa, dxb_ = dx0.clone(), dx0.clone()
+    dga, dba, dgb, dbb = (torch.zeros(d, device="cuda") for _ in range(4))
+    c_a, c_b = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    b_a = torch.empty(M, d, device="cuda", dtype=torch.bfloat16)
+    b_b = torch.empty_like(b_a)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dxa, dga, dba, b_a, dx_colsum=c_a)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dxb_, dgb, dbb, b_b, dx_colsum=c_b, branch_drop=dr)
+    assert torch.equal(dxa, dxb_) and (dga - dgb).abs().max().item() <= 1e-4 * float(dga.abs().max())   # dgamma: atomics
+    assert torch.equal(b_b, (dxb_ * mult).to(torch.bfloat16))
+    assert (c_b - (dxb_ * mult).sum(0)).abs().max().item() < 2e-2 * max(1.0, float((dxb_ * mult).sum(0).abs().max()))
+
+
+@pytest.mark.parametrize("B,S,H,dh,S_valid", [(2, 200, 3, 32, 200), (2, 130, 2, 64, 120), (1, 64, 1, 128, 64), (3, 96, 2, 16, 96)])
+def test_attention_dropout_fwd_bwd(ops, B, S, H, dh, S_valid):
+    from neko_b200._lib import Dropout
+    d = H * dh
+    dr = Dropout.make(_seed(31, 32), 5, 0.2)
+    qkv = _rand((B, S, 3 * d), 11, 0.7, torch.bfloat16)
+    fv = torch.tensor([0, 17, 5][:B], dtype=torch.int32, device="cuda")
+    out, lse = ops.attention_fwd(qkv, fv, H, S_valid, drop=dr)
+    mult = (ops.dropout_mask(B * H * S, S, dr, "cuda").float() * dr.scale).view(B, H, S, S)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = (t.view(B, S, H, dh).transpose(1, 2) for t in qf.split(d, dim=2))
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    idx = torch.arange(S, device="cuda")
+    ok = (idx[None, :] <= idx[:, None])[None, None] & (idx[None, None, None, :] >= fv[:, None, None, None])
+    sc = sc.masked_fill(~ok, float("-inf"))
+    pr = torch.softmax(sc, -1).nan_to_num(0.0) * mult
+    ref = (pr @ v).transpose(1, 2).reshape(B, S, d)
+    live = (idx[None, :] >= fv[:, None]) & (idx[None, :] < S_valid)
+    assert (out.float() - ref)[live].abs().max().item() < 3e-2
+    dout = _rand((B, S, d), 12, 1.0, torch.bfloat16) * live[..., None]
+    (ref * live[..., None]).backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, fv, H, S_valid, drop=dr)
+    g = qf.grad
+    rel = ((dqkv.float() - g)[live].norm() / g[live].norm()).item()
+    assert rel < 3e-2, rel

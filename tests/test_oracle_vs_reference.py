@@ -61,3 +61,54 @@ def test_continuous_tokenizer_random_sweep():
         tok = ContinuousTokenizer(use_mu_law=mu_law, mu=100, M=256, n_bins=1024, offset=50257)
         ref = tok.encode(torch.from_numpy(x.copy())).numpy()
         assert np.array_equal(ref, O.discretize(x, mu_law, cfg))
+
+
+def test_dropout_sites_match_reference():
+    """Pins WHERE the oracle applies its explicit dropout multipliers: the reference runs in train mode with
+    nn.Dropout.forward replaced by a recorded Bernoulli mask per call (call order: embeddings, then per layer attention
+    weights / attention residual / MLP residual); the oracle replays the same masks."""
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=64, text_tokens=200)
+    w = O.make_weights(cfg, seed=5)
+    rs = np.random.RandomState(5)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+    batch = [
+        dict(continuous_obs=f32(rs.standard_normal((4, 3)) * 4), continuous_actions=f32(np.clip(rs.standard_normal((4, 2)), -1, 1))),
+        dict(text=rs.randint(0, 200, (17,)).tolist()),
+    ]
+    ref_shim.set_text_vocab(cfg.text_tokens)
+    G = ref_shim.load_reference_policy_class()
+    m = G(device="cpu", embed_dim=cfg.embed_dim, layers=cfg.layers, heads=cfg.heads, dropout=0.25, resid_mid_channels=128,
+          context_len=cfg.context_len, pad_seq=cfg.pad_seq)
+    m.load_state_dict(w, strict=False)
+    m.train()
+    gen = torch.Generator().manual_seed(77)
+    calls = []
+
+    def fake_dropout(self, x):
+        if not self.training or self.p == 0:
+            return x
+        mult = (torch.rand(x.shape, generator=gen) >= self.p).to(x.dtype) / (1.0 - self.p)
+        calls.append(mult)
+        return x * mult
+
+    orig = torch.nn.Dropout.forward
+    torch.nn.Dropout.forward = fake_dropout
+    try:
+        logits, loss = m(batch, compute_loss=True)
+    finally:
+        torch.nn.Dropout.forward = orig
+    loss.backward()
+    assert len(calls) == 1 + 3 * cfg.layers
+    assert m.transformer.drop.p == 0.1            # SURVEY quirk 8: embd_pdrop ignores --dropout
+    drop = {"embd": calls[0]}
+    for i in range(cfg.layers):
+        drop[("attn", i)], drop[("resid_attn", i)], drop[("resid_mlp", i)] = calls[1 + 3 * i:4 + 3 * i]
+    for t in w.values():
+        t.requires_grad_(True)
+    out = O.forward(w, batch, cfg, compute_loss=True, training=True, drop=drop)
+    out.loss.backward()
+    assert (logits - out.logits).abs().max().item() <= 1e-5
+    assert abs(loss.item() - out.loss.item()) <= 1e-6
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - w[n].grad).abs().max().item() <= 1e-5 * max(1.0, float(p.grad.abs().max())), n

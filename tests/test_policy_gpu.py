@@ -313,3 +313,54 @@ def test_cuda_graph_replay_matches_eager():
     for (n, pe), (_, pg) in zip(eager.named_parameters(), graph.named_parameters()):
         if pe.grad is not None:
             assert (pe.grad - pg.grad).abs().max().item() <= 1e-5 * (pe.grad.abs().max().item() + 1e-12) + 1e-9, n
+
+
+# ---------------------------------------------------------------------------------------------------
+# dropout (trajectory_gpt2.py:179,254,278,707): the kernels' counter-based masks are extracted and the step is replayed
+# in the oracle with exactly those masks -> same parity gates as the dropout-free step
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,graphs", [("mixed", False), ("dh128", False), ("mixed", True)])
+def test_train_step_with_dropout_matches_oracle_replay(case, graphs):
+    cfg = O.GatoConfig(**SMALL_CASES[case]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w, train=True)
+    m.transformer.drop.p = 0.1                       # the reference's embd_pdrop
+    for blk in m.transformer.h:
+        blk.attn.attn_dropout.p = 0.2
+        blk.attn.resid_dropout.p = 0.15
+        blk.mlp.dropout.p = 0.15
+    m.use_cuda_graphs = graphs
+    batch = small_batch(case, cfg.text_tokens)
+    seen = []
+    for it in range(3 if graphs else 1):             # graphs: eager, capture, replay -- fresh masks every time
+        m.zero_grad()
+        torch.manual_seed(77)
+        logits, loss = m(batch, compute_loss=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        drop = {k: v.cpu() for k, v in m.dropout_multipliers().items()}
+        assert len(drop) == 1 + 3 * cfg.layers
+        seen.append(drop["embd"])
+        keep_rate = float((drop["embd"] > 0).float().mean())
+        assert abs(keep_rate - 0.9) < 0.02, keep_rate
+    if graphs:
+        assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    for t in w.values():
+        t.requires_grad_(True)
+    torch.manual_seed(77)
+    ref = O.forward(w, batch, cfg, compute_loss=True, training=True, drop=drop)
+    ref.loss.backward()
+    valid = ref.token_masks.bool()
+    lerr = (logits.detach().cpu() - ref.logits.detach())[valid].abs().max().item()
+    assert lerr <= LOGIT_TOL, f"logits max-abs {lerr}"
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    rep = _grad_report(m, w)
+    bad = {n: v for n, v in rep.items() if v[2] > 1e-6 and (v[0] < 0.99 or v[1] > 0.12)}
+    assert not bad, f"gradient mismatch (cos, rel, ref-norm): {bad}"
+    tight = [v for n, v in rep.items() if n.endswith("c_fc.weight") or n.endswith("c_attn.weight") or n == "predict_token.weight"]
+    assert min(v[0] for v in tight) > 0.999
+    # eval mode ignores every p
+    m.eval()
+    l1, _ = m(batch, compute_loss=False)
+    l2, _ = m(batch, compute_loss=False)
+    assert torch.equal(l1, l2) and m.dropout_multipliers() == {}
