@@ -208,6 +208,13 @@ int neko_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stre
 int neko_cast_f32_to_f16(const float* src, uint16_t* dst, int64_t n, void* stream);
 /* one read, two 16-bit copies (fp16 forward operand + bf16 backward operand of the weights) */
 int neko_cast_f32_to_f16_bf16(const float* src, uint16_t* dst_f16, uint16_t* dst_bf16, int64_t n, void* stream);
+/* GEGLU gate (--activation_fn geglu; MLP.forward, trajectory_gpt2.py:267-276): h = gelu(c_fc(x)) * gated_layer(x).
+ * fwd: out (fp16 if out_f16 else bf16, + optional bf16 copy) = act (fp16 if act_f16 else bf16) * gate (bf16), n elements.
+ * bwd: d_gate = dh * gelu_erf(pre), d_pre = dh * gate * gelu_erf'(pre); all bf16. */
+int neko_geglu_fwd(const uint16_t* act, const uint16_t* gate_bf16, uint16_t* out, uint16_t* out_bf16 /* nullable */,
+                   int64_t n, int act_f16, int out_f16, void* stream);
+int neko_geglu_bwd(const uint16_t* dh_bf16, const uint16_t* pre_bf16, const uint16_t* gate_bf16, uint16_t* d_gate_bf16,
+                   uint16_t* d_pre_bf16, int64_t n, void* stream);
 /* out[n] (+)= sum_m X[m,n]; X bf16 [M, ld]  (bias gradients of Conv1D / Linear). */
 int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, int accumulate, void* stream);
 /* rows: dst[i,:] = src[rows[i],:] (gather) or dst[rows[i],:] = src[i,:] (scatter), bf16 width n. */

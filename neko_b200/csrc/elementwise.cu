@@ -106,6 +106,51 @@ __global__ void __launch_bounds__(256) scatter_rows_add_kernel(const bf16* __res
   for (int i = lane; i < n; i += 32) d[i] += __bfloat162float(s[i]);
 }
 
+// ---- GEGLU gate (MLP.forward with gate, trajectory_gpt2.py:267-276): h = gelu(c_fc(x)) * gated_layer(x) ----
+// forward: act (16-bit, format of the GELU output) * gate (bf16) -> product in the forward operand format (+ bf16 copy)
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const uint16_t* __restrict__ act, const bf16* __restrict__ gate,
+                                                        uint16_t* __restrict__ out, uint16_t* __restrict__ out_bf, long long n8,
+                                                        int act_f16, int out_f16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(act)[i];
+    const uint4 g = reinterpret_cast<const uint4*>(gate)[i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4], ob[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 av = act_f16 ? unpack_f16x2(aw[j]) : unpack_bf16x2(aw[j]);
+      const float2 gv = unpack_bf16x2(gw[j]);
+      o[j] = pack_16x2(av.x * gv.x, av.y * gv.y, out_f16 != 0);
+      ob[j] = pack_bf16x2(av.x * gv.x, av.y * gv.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (out_bf) reinterpret_cast<uint4*>(out_bf)[i] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+  }
+}
+// backward: dh (bf16) -> d_gate = dh * gelu(pre), d_pre = dh * gate * gelu'(pre)
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ pre,
+                                                        const bf16* __restrict__ gate, bf16* __restrict__ d_gate,
+                                                        bf16* __restrict__ d_pre, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 dv = reinterpret_cast<const uint4*>(dh)[i];
+    const uint4 pv = reinterpret_cast<const uint4*>(pre)[i];
+    const uint4 gv = reinterpret_cast<const uint4*>(gate)[i];
+    const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t og[4], op[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 d2 = unpack_bf16x2(dw[j]), p2 = unpack_bf16x2(pw[j]), g2 = unpack_bf16x2(gw[j]);
+      float y0, y1, s0, s1;
+      gelu_erf_both(p2.x, y0, s0);
+      gelu_erf_both(p2.y, y1, s1);
+      og[j] = pack_bf16x2(d2.x * y0, d2.y * y1);
+      op[j] = pack_bf16x2(d2.x * g2.x * s0, d2.y * g2.y * s1);
+    }
+    reinterpret_cast<uint4*>(d_gate)[i] = make_uint4(og[0], og[1], og[2], og[3]);
+    reinterpret_cast<uint4*>(d_pre)[i] = make_uint4(op[0], op[1], op[2], op[3]);
+  }
+}
+
 // ---- dropout on an fp32 [rows, cols] tensor in place (embd dropout and its backward), and the mask itself ----
 __global__ void __launch_bounds__(256) dropout_apply_kernel(float* __restrict__ x, long long ld, int rows, int cols, DropCfg drop) {
   const uint32_t key = drop_key(drop);
@@ -246,6 +291,34 @@ int neko_dropout_mask(uint8_t* keep, int rows, int cols, const neko_dropout* dro
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
   dropout_mask_kernel<<<blocks, 256, 0, as_stream(stream)>>>(keep, rows, cols, c);
   NEKO_LAUNCH_CHECK("dropout_mask_kernel");
+  return NEKO_OK;
+}
+
+int neko_geglu_fwd(const uint16_t* act, const uint16_t* gate_bf16, uint16_t* out, uint16_t* out_bf16, int64_t n, int act_f16,
+                   int out_f16, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(act && gate_bf16 && out && n > 0 && n % 8 == 0, "geglu_fwd: bad arguments (n must be a multiple of 8)");
+  NEKO_REQUIRE(((reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(gate_bf16) | reinterpret_cast<uintptr_t>(out) |
+                 reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0, "geglu_fwd: misaligned buffers");
+  const long long n8 = n / 8;
+  const int blocks = (int)std::min<long long>((n8 + 255) / 256, (long long)sm_count() * 16);
+  geglu_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(act, reinterpret_cast<const bf16*>(gate_bf16), out, out_bf16, n8, act_f16, out_f16);
+  NEKO_LAUNCH_CHECK("geglu_fwd_kernel");
+  return NEKO_OK;
+}
+
+int neko_geglu_bwd(const uint16_t* dh_bf16, const uint16_t* pre_bf16, const uint16_t* gate_bf16, uint16_t* d_gate_bf16,
+                   uint16_t* d_pre_bf16, int64_t n, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(dh_bf16 && pre_bf16 && gate_bf16 && d_gate_bf16 && d_pre_bf16 && n > 0 && n % 8 == 0, "geglu_bwd: bad arguments");
+  NEKO_REQUIRE(((reinterpret_cast<uintptr_t>(dh_bf16) | reinterpret_cast<uintptr_t>(pre_bf16) | reinterpret_cast<uintptr_t>(gate_bf16) |
+                 reinterpret_cast<uintptr_t>(d_gate_bf16) | reinterpret_cast<uintptr_t>(d_pre_bf16)) & 15) == 0, "geglu_bwd: misaligned buffers");
+  const long long n8 = n / 8;
+  const int blocks = (int)std::min<long long>((n8 + 255) / 256, (long long)sm_count() * 16);
+  geglu_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(dh_bf16), reinterpret_cast<const bf16*>(pre_bf16),
+                                                          reinterpret_cast<const bf16*>(gate_bf16), reinterpret_cast<bf16*>(d_gate_bf16),
+                                                          reinterpret_cast<bf16*>(d_pre_bf16), n8);
+  NEKO_LAUNCH_CHECK("geglu_bwd_kernel");
   return NEKO_OK;
 }
 

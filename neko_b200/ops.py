@@ -109,6 +109,18 @@ def layernorm_bwd(dy_bf16, x, gamma, mean, rstd, dx_resid, dgamma, dbeta, dx_bf1
           "neko_layernorm_bwd")
 
 
+def geglu_fwd(act: torch.Tensor, gate: torch.Tensor, out: torch.Tensor, out_bf16: Optional[torch.Tensor] = None):
+    """out = act * gate (MLP gate of --activation_fn geglu)."""
+    assert gate.dtype == torch.bfloat16 and act.is_contiguous() and gate.is_contiguous() and out.is_contiguous()
+    check(load().neko_geglu_fwd(_p(act), _p(gate), _p(out), _p(out_bf16), C.c_int64(act.numel()), C.c_int(int(act.dtype == torch.float16)),
+                                C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_geglu_fwd")
+    return out
+
+
+def geglu_bwd(dh: torch.Tensor, pre: torch.Tensor, gate: torch.Tensor, d_gate: torch.Tensor, d_pre: torch.Tensor):
+    check(load().neko_geglu_bwd(_p(dh), _p(pre), _p(gate), _p(d_gate), _p(d_pre), C.c_int64(dh.numel()), stream_ptr()), "neko_geglu_bwd")
+
+
 def dropout_apply(x: torch.Tensor, drop: Optional[Dropout]):
     """x fp32 [rows, cols] *= mask * scale, in place (embd dropout, trajectory_gpt2.py:707, and its backward)."""
     if drop is None or not drop.thr16:

@@ -51,6 +51,11 @@ class _EmbeddingParams(nn.Module):
         self.weight = nn.Parameter(torch.empty(n, d))
         nn.init.normal_(self.weight, 0.0, std)
 
+    def forward(self, idx: torch.Tensor) -> torch.Tensor:
+        """Row lookup for callers outside the fused path (the predict_* loops embed one generated token at a time,
+        gato_policy.py:465,600); training gathers rows inside tokenize_embed_kernel instead."""
+        return self.weight.detach()[idx.to(self.weight.device).long()]
+
 
 class ResidualBlock_V2(nn.Module):
     """embeddings.py:111-131: conv1 (3->C) / gn2 (groups, C) / conv2 (C->3); gn1 is Identity."""

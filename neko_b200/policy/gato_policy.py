@@ -473,6 +473,90 @@ class GatoPolicy(nn.Module):
                 state.mask.view(B, W).clone())
 
     # ------------------------------------------------------------------------------------------
+    # inference loops (gato_policy.py:444-616).  Same call pattern as the reference: every generated token re-runs the
+    # context through forward(); the host logic below only picks tokens and grows the context.
+    # ------------------------------------------------------------------------------------------
+    def _pick(self, row: torch.Tensor, deterministic: bool) -> torch.Tensor:
+        if deterministic:
+            return torch.argmax(row, dim=-1)
+        return torch.multinomial(torch.softmax(row, dim=-1), num_samples=1)[0]
+
+    def _generate(self, token_embeddings, token_masks, n_tokens: int, lo: int, hi: int, deterministic: bool):
+        """Autoregressive continuation on caller-owned embeddings: logits of the last position restricted to ids
+        [lo, hi], pick, embed the pick, append, trim to context_len (gato_policy.py:452-476 and :586-605)."""
+        rows, picked = [], []
+        for _ in range(n_tokens):
+            logits, _ = self.forward(token_embeddings=token_embeddings, token_masks=token_masks, token_target_masks=None, tokens=None)
+            row = logits[0, -1, lo:hi + 1]
+            rows.append(row)
+            tok = self._pick(row, deterministic) + lo
+            token_masks = torch.cat([token_masks, torch.ones(token_masks.shape[0], 1, device=self.device)], dim=1)
+            token_embeddings = torch.cat([token_embeddings, self.embed_token(tok).reshape(1, 1, -1)], dim=1)
+            token_embeddings = token_embeddings[:, -self.context_len:, :]
+            token_masks = token_masks[:, -self.context_len:]
+            picked.append(tok)
+        return rows, picked
+
+    def predict_text(self, batch_dict, max_length=20, deterministic=True):
+        """gato_policy.py:444-478 -> (logits [max_length, text_tokens], list of predicted token ids)."""
+        lo, hi = self.token_starts["text"], self.token_ends["text"]
+        with torch.no_grad():
+            emb, _, _, masks = self.tokenize_input_dicts([batch_dict])
+            rows, picked = self._generate(emb, masks, max_length, lo, hi, deterministic)
+        return torch.stack(rows, dim=0), picked
+
+    def predict_response(self, image, prompt_tokens=[], max_length=128, deterministic=True):  # noqa: B006 - reference signature
+        """gato_policy.py:484-544: caption / answer generation from one image; the image is embedded once and passed as
+        ``image_embeddings``, the growing text as token ids.  Returns (logits [max_length, text_tokens], decoded text)."""
+        lo, hi = self.token_starts["text"], self.token_ends["text"]
+        with torch.no_grad():
+            image_embeddings = self.image_embedding(image.to(self.device))
+            assert image_embeddings.shape[0] == 1, "number of images should always be 1 for predicting response"
+            n_patches = image_embeddings.shape[1]
+            rows, response = [], []
+            prompt = list(prompt_tokens)
+            for idx in range(max_length):
+                batch = {"image_embeddings": image_embeddings, "text": torch.tensor(prompt + response, dtype=torch.long)}
+                logits, _ = self.forward([batch])
+                assert logits.shape[0] == 1, "batch size should always be 1 for predicting response"
+                # the last image patch predicts the first text token, each text token the next one
+                row = logits[0, n_patches - 1 + len(prompt) + idx, lo:hi + 1]
+                rows.append(row)
+                response.append(int(self._pick(row, deterministic)))
+        return torch.stack(rows, dim=0), self.text_tokenizer.decode(response)
+
+    def predict_caption(self, image, max_length=128, deterministic=True):
+        return self.predict_response(image, prompt_tokens=[], max_length=max_length, deterministic=deterministic)
+
+    def predict_answer(self, image, question, max_length=16, deterministic=True):
+        return self.predict_response(image, prompt_tokens=self.text_tokenizer.encode(question), max_length=max_length,
+                                     deterministic=deterministic)
+
+    def predict_control(self, input: dict, task, deterministic: bool = True):  # noqa: A002 - reference signature
+        """gato_policy.py:557-616: one action for a control task.  ``input`` carries one padded action timestep at the
+        end; its tokens are dropped and re-generated, restricted to the task's action vocabulary."""
+        kind = getattr(task.action_type, "__name__", str(task.action_type))
+        action_tokens = task.action_tokens
+        if "Discrete" in kind:
+            which = "discrete"
+            assert action_tokens == 1, "only support 1 discrete action token"
+        elif "Box" in kind:
+            which = "continuous"
+        else:
+            raise ValueError(f"unsupported action space {kind}")
+        lo, hi = self.token_starts[which], self.token_ends[which]
+        if which == "discrete":
+            assert task.env.action_space.n <= self.discrete_tokens, "discrete action space too large for model"
+            hi = lo + task.env.action_space.n - 1
+        with torch.no_grad():
+            emb, _, _, masks = self.tokenize_input_dicts([input])
+            emb, masks = emb[:, :-action_tokens, :], masks[:, :-action_tokens]
+            _, picked = self._generate(emb, masks, action_tokens, lo, hi, deterministic)
+        if which == "discrete":
+            return picked[0] - lo
+        return self.continuous_action_tokenizer.decode(torch.stack(picked, dim=0))
+
+    # ------------------------------------------------------------------------------------------
     # planning + upload
     # ------------------------------------------------------------------------------------------
     def _plan(self, inputs, compute_loss) -> _State:
@@ -686,8 +770,7 @@ class GatoPolicy(nn.Module):
 
     def _decoder(self, st: _State, x: torch.Tensor, B: int, W: int, S_valid: int, first_valid: torch.Tensor, keep: bool):
         """L pre-LN blocks + ln_f (trajectory_gpt2.py:322-358, 779).  x fp32 [N,d] -> hf bf16 [N,d]."""
-        if self.transformer.config.gate:
-            raise NotImplementedError("activation_fn='geglu' (SURVEY.md section 8(f).4) is not implemented in the CUDA path")
+        gate = bool(self.transformer.config.gate)
         d, H = self.embed_dim, self.heads
         N = B * W
         eps = self.transformer.config.layer_norm_epsilon
@@ -728,14 +811,25 @@ class GatoPolicy(nn.Module):
             ops.layernorm_fwd(x1, blk.ln_2.weight, blk.ln_2.bias, eps, ln2, m2, r2, y2=ln2_b if dual else None)
             fpre = self._buf("fpre" + tag, (N, 4 * d), torch.bfloat16)
             fact, fact_b = pair("fact", tag, (N, 4 * d))
-            ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
-                     out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias)
+            fgate = None
+            if not gate:
+                ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
+                         out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias)
+            else:   # geglu: h = gelu(c_fc(x)) * gated_layer(x)   (trajectory_gpt2.py:267-276; nn.Linear weight is [out, in])
+                gelu_o = self._buf("fgelu", (N, 4 * d), fdt)
+                ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=gelu_o,
+                         bias=blk.mlp.c_fc.bias)
+                fgate = self._buf("fgate" + tag, (N, 4 * d), torch.bfloat16)
+                ops.gemm(ln2, self._wview(pre + "mlp.gated_layer.weight"), epilogue=ops.EPI_BF16, out=fgate,
+                         bias=blk.mlp.gated_layer.bias)
+                ops.geglu_fwd(gelu_o, fgate, fact, fact_b if dual else None)
+                self.launches += 2
             x2 = self._buf(f"x.{2 * i + 2}" if keep else "x.a", (N, d), torch.float32)
             ops.gemm(fact, self._wview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
                      bias=blk.mlp.c_proj.bias, drop=self._drop_site(st, 4 * i + 3, blk.mlp.dropout.p))
             self.launches += 7
             if keep:
-                acts.append((x, ln1_b, m1, r1, qkv, att_b, lse, x1, ln2_b, m2, r2, fpre, fact_b))
+                acts.append((x, ln1_b, m1, r1, qkv, att_b, lse, x1, ln2_b, m2, r2, fpre, fact_b, fgate))
             x = x2
         hf, hf_b = pair("hf", "", (N, d))
         mf = self._buf("mf", (N,), torch.float32)
@@ -982,17 +1076,34 @@ class GatoPolicy(nn.Module):
         for i in reversed(range(self.layers)):
             blk = self.transformer.h[i]
             pre = f"transformer.h.{i}."
-            (x0, ln1, m1, r1, qkv, att, lse, x1, ln2, m2, r2, fpre, fact) = st.acts[i]
+            (x0, ln1, m1, r1, qkv, att, lse, x1, ln2, m2, r2, fpre, fact, fgate) = st.acts[i]
             # MLP: x2 = x1 + gelu(ln2 @ Wfc + b) @ Wproj + b
             ops.gemm(fact, dxb, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_proj.weight"), accumulate=acc,
                      M=4 * d, N=d, K=N)
             dpre = self._buf("dfpre", (N, 4 * d), torch.bfloat16)
-            ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre)
+            dln = self._buf("dln", (N, d), torch.bfloat16)
+            if fgate is None:
+                ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre)
+            else:   # geglu: dh -> (d_gate, d_pre); the gate Linear gets its own wgrad / bias grad / dgrad
+                dh4 = self._buf("dfh", (N, 4 * d), torch.bfloat16)
+                ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_BF16, out=dh4)
+                dgate = self._buf("dfgate", (N, 4 * d), torch.bfloat16)
+                ops.geglu_bwd(dh4, fpre, fgate, dgate, dpre)
+                ops.gemm(dgate, ln2, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.gated_layer.weight"),
+                         accumulate=True, M=4 * d, N=d, K=N)
+                ops.colsum(dgate, G(pre + "mlp.gated_layer.bias"), accumulate=True)
+                self.launches += 4
             ops.gemm(ln2, dpre, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G(pre + "mlp.c_fc.weight"), accumulate=acc,
                      M=d, N=4 * d, K=N)
             ops.colsum(dpre, G(pre + "mlp.c_fc.bias"), accumulate=True)
-            dln = self._buf("dln", (N, d), torch.bfloat16)
-            ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_BF16, out=dln)
+            if fgate is None:
+                ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_BF16, out=dln)
+            else:   # d ln2 = d_pre . Wfc^T + d_gate . Wg: two GEMMs into one fp32 buffer, then the 16-bit copy
+                dln32 = self._buf("dln_f32", (N, d), torch.float32)
+                ops.gemm(dpre, Wb(pre + "mlp.c_fc.weight"), epilogue=ops.EPI_F32, out=dln32)
+                ops.gemm(dgate, Wb(pre + "mlp.gated_layer.weight"), b_mn=True, epilogue=ops.EPI_F32, out=dln32, accumulate=True)
+                ops.cast_bf16(dln32, dln)
+                self.launches += 2
             ops.layernorm_bwd(dln, x1, blk.ln_2.weight, m2, r2, dx, G(pre + "ln_2.weight"), G(pre + "ln_2.bias"), dxb,
                               dx_colsum=G(pre + "attn.c_proj.bias"), branch_drop=D(4 * i + 2, blk.attn.resid_dropout.p))
             # attention: x1 = x0 + attn(ln1 @ Wqkv + b) @ Wproj + b

@@ -460,6 +460,48 @@ def forward(w: Dict[str, torch.Tensor], inputs: Sequence[dict], cfg: GatoConfig,
 
 
 # --------------------------------------------------------------------------------------
+# inference loops (greedy): gato_policy.py:444-478 predict_text, :557-616 predict_control
+# --------------------------------------------------------------------------------------
+def generate(w: Dict[str, torch.Tensor], emb: torch.Tensor, mask: torch.Tensor, cfg: GatoConfig, n_tokens: int, lo: int, hi: int):
+    """Greedy continuation on embeddings (gato_policy.py:452-476 / :586-605): last-position logits restricted to
+    ids [lo, hi] -> argmax -> embed_token row appended -> context trimmed to context_len.  Returns
+    (list of restricted logit rows, list of picked absolute ids)."""
+    rows, picked = [], []
+    for _ in range(n_tokens):
+        hid = decoder(emb, mask, w, cfg)
+        row = F.linear(hid[0, -1], w["predict_token.weight"])[lo:hi + 1]
+        rows.append(row)
+        tok = int(torch.argmax(row)) + lo
+        picked.append(tok)
+        emb = torch.cat([emb, w["embed_token.weight"][tok].reshape(1, 1, -1)], dim=1)[:, -cfg.context_len:, :]
+        mask = torch.cat([mask, torch.ones(mask.shape[0], 1)], dim=1)[:, -cfg.context_len:]
+    return rows, picked
+
+
+def predict_text(w: Dict[str, torch.Tensor], batch_dict: dict, cfg: GatoConfig, max_length: int = 20):
+    tb = tokenize([batch_dict], cfg)
+    emb = embed_and_interleave([batch_dict], tb, w, cfg)
+    rows, picked = generate(w, emb, torch.from_numpy(tb.token_masks), cfg, max_length, 0, cfg.text_tokens - 1)
+    return torch.stack(rows), picked
+
+
+def predict_control(w: Dict[str, torch.Tensor], inp: dict, cfg: GatoConfig, action_tokens: int, discrete_n: Optional[int] = None):
+    """Continuous (discrete_n None): returns decoded actions (2*bin/n_bins - 1, input_tokenizers.py:32-42);
+    discrete: the action index."""
+    tb = tokenize([inp], cfg)
+    emb = embed_and_interleave([inp], tb, w, cfg)[:, :-action_tokens]
+    mask = torch.from_numpy(tb.token_masks)[:, :-action_tokens]
+    cont0 = cfg.text_tokens
+    disc0 = cfg.text_tokens + cfg.continuous_tokens
+    if discrete_n is not None:
+        _, picked = generate(w, emb, mask, cfg, 1, disc0, disc0 + discrete_n - 1)
+        return picked[0] - disc0
+    _, picked = generate(w, emb, mask, cfg, action_tokens, cont0, cont0 + cfg.continuous_tokens - 1)
+    t = torch.tensor(picked, dtype=torch.float32) - cont0
+    return (2 * t) / cfg.continuous_tokens - 1
+
+
+# --------------------------------------------------------------------------------------
 # deterministic weights (numpy MT19937 => identical on every machine, no torch RNG involved)
 # --------------------------------------------------------------------------------------
 def weight_shapes(cfg: GatoConfig) -> Dict[str, tuple]:

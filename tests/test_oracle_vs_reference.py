@@ -112,3 +112,37 @@ def test_dropout_sites_match_reference():
     for n, p in m.named_parameters():
         if p.grad is not None:
             assert (p.grad - w[n].grad).abs().max().item() <= 1e-5 * max(1.0, float(p.grad.abs().max())), n
+
+
+def test_inference_loops_match_reference():
+    """predict_text / predict_control (gato_policy.py:444-478, 557-616) against the oracle's greedy restatement."""
+    import sys
+    import types
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=48, text_tokens=200)
+    w = O.make_weights(cfg, seed=9)
+    m = _ref_model(cfg, w)
+    rs = np.random.RandomState(3)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+    with torch.no_grad():
+        logits, toks = m.predict_text(dict(text=rs.randint(0, 200, (9,)).tolist()), max_length=6, deterministic=True)
+    rs = np.random.RandomState(3)
+    ologits, otoks = O.predict_text(w, dict(text=rs.randint(0, 200, (9,)).tolist()), cfg, max_length=6)
+    assert [int(t) for t in toks] == otoks
+    assert (logits - ologits).abs().max().item() <= 1e-4
+    # control, continuous actions: 3 timesteps, the last action row is padding to be generated
+    gym = sys.modules["gymnasium"]
+    obs, act = f32(rs.standard_normal((3, 5)) * 2), f32(np.clip(rs.standard_normal((3, 2)), -1, 1))
+    task = types.SimpleNamespace(action_type=gym.spaces.Box, action_tokens=2, env=None)
+    with torch.no_grad():
+        a_ref = m.predict_control(dict(continuous_obs=obs.clone(), continuous_actions=act.clone()), task, deterministic=True)
+    a_or = O.predict_control(w, dict(continuous_obs=obs.clone(), continuous_actions=act.clone()), cfg, action_tokens=2)
+    assert torch.equal(a_ref.reshape(-1).float(), a_or.reshape(-1))
+    # control, discrete action restricted to the env's n actions
+    img = f32(rs.randint(0, 256, (2, 3, 32, 32)))
+    dact = torch.from_numpy(rs.randint(0, 4, (2, 1)).astype(np.int32))
+    task = types.SimpleNamespace(action_type=gym.spaces.Discrete, action_tokens=1,
+                                 env=types.SimpleNamespace(action_space=types.SimpleNamespace(n=4)))
+    with torch.no_grad():
+        d_ref = m.predict_control(dict(images=img.clone(), discrete_actions=dact.clone()), task, deterministic=True)
+    d_or = O.predict_control(w, dict(images=img.clone(), discrete_actions=dact.clone()), cfg, action_tokens=1, discrete_n=4)
+    assert int(d_ref) == int(d_or)

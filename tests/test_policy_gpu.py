@@ -114,7 +114,7 @@ def _grad_report(m, w):
     return rep
 
 
-@pytest.mark.parametrize("case", ["mixed", "dh128", "nopos"])
+@pytest.mark.parametrize("case", ["mixed", "dh128", "nopos", "geglu_padseq"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_forward_backward_vs_oracle_and_golden(golden_dir, case, mode):
     g = np.load(os.path.join(golden_dir, f"fwd_{case}_{mode}.npz"))
@@ -151,11 +151,22 @@ def test_forward_backward_vs_oracle_and_golden(golden_dir, case, mode):
     assert min(v[0] for v in tight) > 0.999
 
 
-def test_geglu_not_silently_wrong():
+def test_geglu_gate_parameters_receive_gradients():
+    """--activation_fn geglu (trajectory_gpt2.py:267-276): the gate Linear is part of the arena and of backward."""
     cfg = O.GatoConfig(**SMALL_CASES["geglu_padseq"]["cfg"])
-    m = make_policy(cfg, O.make_weights(cfg, seed=3))
-    with pytest.raises(NotImplementedError):
-        m(small_batch("geglu_padseq", cfg.text_tokens), compute_loss=True)
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w, train=True)
+    batch = small_batch("geglu_padseq", cfg.text_tokens)
+    _, loss = m(batch, compute_loss=True)
+    loss.backward()
+    for t in w.values():
+        t.requires_grad_(True)
+    ref = O.forward(w, batch, cfg, compute_loss=True, training=True)
+    ref.loss.backward()
+    rep = _grad_report(m, w)
+    gates = {n: v for n, v in rep.items() if "gated_layer" in n}
+    assert len(gates) == 2 * cfg.layers
+    assert min(v[0] for v in gates.values()) > 0.995, gates
 
 
 def test_pad_seq_matches_oracle():
@@ -364,3 +375,75 @@ def test_train_step_with_dropout_matches_oracle_replay(case, graphs):
     l1, _ = m(batch, compute_loss=False)
     l2, _ = m(batch, compute_loss=False)
     assert torch.equal(l1, l2) and m.dropout_multipliers() == {}
+
+
+# ---------------------------------------------------------------------------------------------------
+# inference loops (gato_policy.py:444-616) against the oracle's greedy restatement
+# ---------------------------------------------------------------------------------------------------
+def _margin_ok(rows, tol=4 * LOGIT_TOL):
+    """True for the steps whose oracle top-2 margin is larger than the logits tolerance (greedy pick is unambiguous)."""
+    out = []
+    for r in rows:
+        top = torch.topk(r, 2).values
+        out.append(float(top[0] - top[1]) > tol)
+    return out
+
+
+def test_predict_text_and_control_match_oracle():
+    import types
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=48, text_tokens=200)
+    w = O.make_weights(cfg, seed=9)
+    m = make_policy(cfg, w)
+    rs = np.random.RandomState(3)
+    prompt = rs.randint(0, 200, (9,)).tolist()
+    logits, toks = m.predict_text(dict(text=list(prompt)), max_length=6, deterministic=True)
+    ologits, otoks = O.predict_text(w, dict(text=list(prompt)), cfg, max_length=6)
+    assert tuple(logits.shape) == (6, cfg.text_tokens) and len(toks) == 6
+    ok = _margin_ok(list(ologits))
+    for i in range(6):
+        assert (logits[i].cpu() - ologits[i]).abs().max().item() <= LOGIT_TOL
+        if not ok[i]:
+            break                       # ambiguous argmax: later steps may legitimately diverge
+        assert int(toks[i]) == otoks[i]
+    # sampling path runs and stays inside the text vocabulary
+    _, stoks = m.predict_text(dict(text=list(prompt)), max_length=3, deterministic=False)
+    assert all(0 <= int(t) < cfg.text_tokens for t in stoks)
+
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+    obs, act = f32(rs.standard_normal((3, 5)) * 2), f32(np.clip(rs.standard_normal((3, 2)), -1, 1))
+    box = type("Box", (), {})
+    disc = type("Discrete", (), {})
+    task = types.SimpleNamespace(action_type=box, action_tokens=2, env=None)
+    a = m.predict_control(dict(continuous_obs=obs.cuda(), continuous_actions=act.cuda()), task, deterministic=True)
+    a_or = O.predict_control(w, dict(continuous_obs=obs.clone(), continuous_actions=act.clone()), cfg, action_tokens=2)
+    assert tuple(a.shape) == (2,) and float(a.min()) >= -1.0 and float(a.max()) <= 1.0
+    assert (a.cpu().float() - a_or).abs().max().item() <= 2.0 / cfg.continuous_tokens * 8   # within a few bins of the oracle pick
+    img = f32(rs.randint(0, 256, (2, 3, 32, 32)))
+    dact = torch.from_numpy(rs.randint(0, 4, (2, 1)).astype(np.int32))
+    task = types.SimpleNamespace(action_type=disc, action_tokens=1, env=types.SimpleNamespace(action_space=types.SimpleNamespace(n=4)))
+    d = m.predict_control(dict(images=img.cuda(), discrete_actions=dact.cuda()), task, deterministic=True)
+    assert 0 <= int(d) < 4
+
+
+def test_predict_response_runs_on_image_embeddings():
+    cfg = O.GatoConfig(embed_dim=64, layers=1, heads=2, context_len=64, text_tokens=200)
+    w = O.make_weights(cfg, seed=4)
+    m = make_policy(cfg, w)
+
+    class _Txt(_Tok):
+        def decode(self, ids):
+            return " ".join(str(i) for i in ids)
+
+        def encode(self, s):
+            return [int(t) for t in s.split()]
+
+    m.text_tokenizer = _Txt(cfg.text_tokens)
+    rs = np.random.RandomState(8)
+    img = torch.from_numpy(rs.randint(0, 256, (1, 3, 32, 48)).astype(np.uint8))
+    logits, text = m.predict_answer(img, "5 7 11", max_length=4, deterministic=True)
+    assert tuple(logits.shape) == (4, cfg.text_tokens) and len(text.split()) == 4
+    # first generated token: oracle forward on [image, prompt] -> argmax at the last position
+    batch = [dict(images=img.clone(), text=torch.tensor([5, 7, 11]))]
+    ref = O.forward(w, batch, cfg, compute_loss=False)
+    row = ref.logits[0, -2, :cfg.text_tokens]     # position of the last prompt token (the separator follows it)
+    assert (logits[0].cpu() - row).abs().max().item() <= LOGIT_TOL
