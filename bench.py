@@ -51,6 +51,18 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def gemm_traffic(args, launches_per_step):
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed ncu capture of this very command
+    (tools/gemm_traffic.sh -> profiles/r01_gemm_traffic_<cfg>.json); None when no capture matches the configuration."""
+    p = os.path.join(ROOT, "profiles", f"r01_gemm_traffic_{args.config}.json")
+    if args.lean or args.head != "rows" or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("launches") != launches_per_step:
+        return None
+    return round(d["dram_bytes_per_launch"])
+
+
 def gemm_flops_per_step(cfg, N, S, n_rows, head_mode, materialize):
     """Algorithmic GEMM FLOPs actually launched on the tensor-core kernel in one fwd+bwd."""
     d, L, V = cfg["embed_dim"], cfg["layers"], 52352
@@ -348,6 +360,13 @@ def run_ours(args):
     eager_ms = i0.elapsed_time(i1) / inst_steps
     gemm_ms = sum(g[0].elapsed_time(g[1]) for g in gemm_log) / inst_steps * args.steps   # scaled to the timed step count
     gemm_fl = sum(g[2] for g in gemm_log) / inst_steps * args.steps
+
+    def _alg_bytes(key):   # operands once + outputs once (+ the auxiliary read of the residual / GELU' epilogues)
+        M_, N_, K_, _am, _bm, epi = key
+        out = {0: 2, 1: 4, 2: 6, 3: 8, 4: 4, 5: 10}[epi]
+        return 2.0 * M_ * K_ + 2.0 * N_ * K_ + float(out) * M_ * N_
+    gemm_alg_bytes = sum(_alg_bytes(g[3]) for g in gemm_log) / max(len(gemm_log), 1)
+    gemm_launches_per_step = len(gemm_log) // inst_steps
     if args.gemm_report and rank == 0:
         agg = {}
         for g in gemm_log:
@@ -405,7 +424,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(achieved / peak_tf, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak_tf, 4) if achieved else None,
+                     "traffic": gemm_traffic(args, gemm_launches_per_step), "traffic_unit": "DRAM bytes per GEMM launch (ncu, mean over the step's launches)",
+                     "algorithmic_bytes_per_launch": round(gemm_alg_bytes), "gemm_launches_per_step": gemm_launches_per_step,
+                     "peak_source": peak_src,
                      "gemm_ms_per_step": round(gemm_ms / args.steps, 4), "gemm_share_of_step": round(gemm_ms / args.steps / eager_ms, 4),
                      "timing": "CUDA events around each GEMM launch in an eager pass of the same step run right after the timed region "
                                f"(eager step {eager_ms:.3f} ms; the timed region replays CUDA graphs)",
@@ -415,7 +437,7 @@ def run_ours(args):
         os.unlink(clk.name)
     except OSError:
         pass
-    if world == 1:
+    if world == 1 and not args.no_front_end:
         out["front_end"] = front_end_roofline(model, host_batch, dev, cfgd, args.config)
     if world == 1 and not args.no_cpu_baseline:
         sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
@@ -438,6 +460,7 @@ def main():
     ap.add_argument("--head", default="rows", choices=["dense", "rows"], help="head backward: dense like the reference's autograd, or loss rows only (identical gradients)")
     ap.add_argument("--lean", action="store_true", help="evaluate the LM head on loss rows only (forward returns no logits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-front-end", action="store_true", help="skip the tokeniser / image-stack HBM roofline pass")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step from CUDA graphs")
     ap.add_argument("--graph-probe", action="store_true", help="experiment: replay the step from a CUDA graph")
     ap.add_argument("--gemm-report", action="store_true", help="per-shape GEMM timings (CUDA events) on stderr")

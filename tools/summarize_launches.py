@@ -17,9 +17,12 @@ for r in csv.DictReader(lines):
 # keep the launches of the last step
 starts = [i for i, r in enumerate(rows) if "tokenize_embed" in r[0]]
 if len(starts) >= 2:
-    # one period of the launch sequence: from the previous step's tokenize marker up to this step's (the image-embedding
-    # and weight-cast launches that precede the marker belong to the period's tail; every step launches the same list)
-    rows = rows[starts[-2]:starts[-1]]
+    # one period of the launch sequence: from one step's tokenize marker up to the next one's (the image-embedding
+    # and weight-cast launches that precede the marker belong to the period's tail; every step launches the same list).
+    # The last full period counts; back-to-back markers (bench.py's front-end timing loop) are skipped.
+    wins = [(a, b) for a, b in zip(starts[:-1], starts[1:]) if b - a > 20]
+    if wins:
+        rows = rows[wins[-1][0]:wins[-1][1]]
 agg = OrderedDict()
 for k, ns, _g in rows:
     name = k.split("(")[0]
