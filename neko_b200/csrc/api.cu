@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace neko {
@@ -19,6 +20,15 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return NEKO_OK;
   set_error("%s: %s", what, cudaGetErrorString(e));
   return NEKO_ECUDA;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("NEKO_PDL");
+    cached = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return cached == 1;
 }
 
 int sm_count() {

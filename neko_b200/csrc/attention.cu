@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
                                                                bf16* __restrict__ out, bf16* __restrict__ out2, float* __restrict__ lse, int S,
                                                                int S_valid, int H, float scale_log2, int out_f16, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sQ{s0};
   auto sK = [&](int bi) { return Tile<DH>{s0 + (1 + bi) * Tile<DH>::BYTES}; };  // double-buffered K / V tiles
@@ -173,15 +175,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
       const float ref_a = (mn_a == -INFINITY) ? 0.f : mn_a * scale_log2;
       const float ref_b = (mn_b == -INFINITY) ? 0.f : mn_b * scale_log2;
-      const float corr_a = exp2f(m_a * scale_log2 - ref_a), corr_b = exp2f(m_b * scale_log2 - ref_b);
+      const float corr_a = ex2_ftz(m_a * scale_log2 - ref_a), corr_b = ex2_ftz(m_b * scale_log2 - ref_b);
       m_a = mn_a; m_b = mn_b;
       float sum_a = 0.f, sum_b = 0.f;
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
-        s[n][0] = exp2f(fmaf(s[n][0], scale_log2, -ref_a));
-        s[n][1] = exp2f(fmaf(s[n][1], scale_log2, -ref_a));
-        s[n][2] = exp2f(fmaf(s[n][2], scale_log2, -ref_b));
-        s[n][3] = exp2f(fmaf(s[n][3], scale_log2, -ref_b));
+        s[n][0] = ex2_ftz(fmaf(s[n][0], scale_log2, -ref_a));
+        s[n][1] = ex2_ftz(fmaf(s[n][1], scale_log2, -ref_a));
+        s[n][2] = ex2_ftz(fmaf(s[n][2], scale_log2, -ref_b));
+        s[n][3] = ex2_ftz(fmaf(s[n][3], scale_log2, -ref_b));
         sum_a += s[n][0] + s[n][1];
         sum_b += s[n][2] + s[n][3];
       }
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
                                                                   bf16* __restrict__ dqkv, int S, int S_valid, int H, float scale,
                                                                   float scale_log2, int out_f16, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sQ{s0};
   const Tile<DH> sdO{s0 + Tile<DH>::BYTES};
@@ -364,14 +368,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
           mma_bf16(dp[2 * n2 + 1], doa[k], vb[2], vb[3]);
         }
       }
+      // interior tiles (all keys valid and strictly below every query of the tile) need no per-element predicate
+      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0) || (q0 + ATT_BLK > S_valid);
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
-        const int key = j0 + n * 8 + 2 * q;
-        const bool va = row_a < S_valid, vb = row_b < S_valid;
-        const float p0 = (va && key >= lo && key <= row_a) ? exp2f(fmaf(s[n][0], scale_log2, -lse_a)) : 0.f;
-        const float p1 = (va && key + 1 >= lo && key + 1 <= row_a) ? exp2f(fmaf(s[n][1], scale_log2, -lse_a)) : 0.f;
-        const float p2 = (vb && key >= lo && key <= row_b) ? exp2f(fmaf(s[n][2], scale_log2, -lse_bb)) : 0.f;
-        const float p3 = (vb && key + 1 >= lo && key + 1 <= row_b) ? exp2f(fmaf(s[n][3], scale_log2, -lse_bb)) : 0.f;
+        float p0 = ex2_ftz(fmaf(s[n][0], scale_log2, -lse_a)), p1 = ex2_ftz(fmaf(s[n][1], scale_log2, -lse_a));
+        float p2 = ex2_ftz(fmaf(s[n][2], scale_log2, -lse_bb)), p3 = ex2_ftz(fmaf(s[n][3], scale_log2, -lse_bb));
+        if (need_mask) {
+          const int key = j0 + n * 8 + 2 * q;
+          const bool va = row_a < S_valid, vb = row_b < S_valid;
+          if (!(va && key >= lo && key <= row_a)) p0 = 0.f;
+          if (!(va && key + 1 >= lo && key + 1 <= row_a)) p1 = 0.f;
+          if (!(vb && key >= lo && key <= row_b)) p2 = 0.f;
+          if (!(vb && key + 1 >= lo && key + 1 <= row_b)) p3 = 0.f;
+        }
         if (DROP) {
           const uint32_t pr = (uint32_t)((j0 + n * 8) >> 1) + q;
           float m0, m1;
@@ -424,6 +434,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
                                                                    const int32_t* __restrict__ first_valid, bf16* __restrict__ dqkv,
                                                                    int S, int S_valid, int H, float scale, float scale_log2, DropCfg drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const Tile<DH> sK{s0};
   const Tile<DH> sV{s0 + Tile<DH>::BYTES};
@@ -505,6 +517,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         }
       }
       // P^T = exp(S^T * scale - lse[query]); dS^T = P^T * (dP^T - delta[query]) * scale
+      const bool need_mask = (j0 < lo) || (i0 < j0 + ATT_BLK) || (i0 + ATT_BLK > S_valid);
       const float* lsp = s_lse + buf * ATT_BLK;
       const float* dlp = s_delta + buf * ATT_BLK;
 #pragma unroll
@@ -512,14 +525,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         const int c0 = n * 8 + 2 * q;  // local query column
         const int qi0 = i0 + c0, qi1 = qi0 + 1;
         const float l0 = lsp[c0], l1 = lsp[c0 + 1];
-        const bool ok00 = (key_a >= lo) && (key_a <= qi0) && (qi0 < S_valid);
-        const bool ok01 = (key_a >= lo) && (key_a <= qi1) && (qi1 < S_valid);
-        const bool ok10 = (key_b >= lo) && (key_b <= qi0) && (qi0 < S_valid);
-        const bool ok11 = (key_b >= lo) && (key_b <= qi1) && (qi1 < S_valid);
-        const float p00 = ok00 ? exp2f(fmaf(st[n][0], scale_log2, -l0)) : 0.f;
-        const float p01 = ok01 ? exp2f(fmaf(st[n][1], scale_log2, -l1)) : 0.f;
-        const float p10 = ok10 ? exp2f(fmaf(st[n][2], scale_log2, -l0)) : 0.f;
-        const float p11 = ok11 ? exp2f(fmaf(st[n][3], scale_log2, -l1)) : 0.f;
+        float p00 = ex2_ftz(fmaf(st[n][0], scale_log2, -l0)), p01 = ex2_ftz(fmaf(st[n][1], scale_log2, -l1));
+        float p10 = ex2_ftz(fmaf(st[n][2], scale_log2, -l0)), p11 = ex2_ftz(fmaf(st[n][3], scale_log2, -l1));
+        if (need_mask) {   // diagonal tile, left padding inside the key tile, or right padding inside the query tile
+          if (!((key_a >= lo) && (key_a <= qi0) && (qi0 < S_valid))) p00 = 0.f;
+          if (!((key_a >= lo) && (key_a <= qi1) && (qi1 < S_valid))) p01 = 0.f;
+          if (!((key_b >= lo) && (key_b <= qi0) && (qi0 < S_valid))) p10 = 0.f;
+          if (!((key_b >= lo) && (key_b <= qi1) && (qi1 < S_valid))) p11 = 0.f;
+        }
         const float d0 = dlp[c0], d1 = dlp[c0 + 1];
         float m00 = 1.f, m01 = 1.f, m10 = 1.f, m11 = 1.f;
         if (DROP) {  // element (query, key): bits of key pair (key >> 1), half-word key & 1
@@ -596,7 +609,7 @@ static int launch_fwd(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2,
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn_fwd)");
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_fwd_kernel<DH, DROP><<<grid, ATT_THREADS, smem, st>>>(qkv, fv, out, out2, lse, S, S_valid, H, scale_log2, out_f16, drop);
+  launch_pdl(attn_fwd_kernel<DH, DROP>, grid, dim3(ATT_THREADS), smem, st, qkv, fv, out, out2, lse, S, S_valid, H, scale_log2, out_f16, drop);
   NEKO_LAUNCH_CHECK("attn_fwd_kernel");
   return NEKO_OK;
 }
@@ -612,9 +625,9 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
   const float scale = 1.0f / sqrtf((float)DH);
   const float scale_log2 = 1.4426950408889634f * scale;
   dim3 grid((S + ATT_BLK - 1) / ATT_BLK, H, B);
-  attn_bwd_dq_kernel<DH, DROP><<<grid, ATT_THREADS, s1, st>>>(qkv, out, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, out_f16, drop);
+  launch_pdl(attn_bwd_dq_kernel<DH, DROP>, grid, dim3(ATT_THREADS), s1, st, qkv, out, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, out_f16, drop);
   NEKO_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<DH, DROP><<<grid, ATT_THREADS, s2, st>>>(qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, drop);
+  launch_pdl(attn_bwd_dkv_kernel<DH, DROP>, grid, dim3(ATT_THREADS), s2, st, qkv, dout, lse, delta, fv, dqkv, S, S_valid, H, scale, scale_log2, drop);
   NEKO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return NEKO_OK;
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/neko_b200.h"
 
@@ -30,6 +31,28 @@ int check_cuda(cudaError_t e, const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// Kernels launched through launch_pdl() may be scheduled while the previous kernel of the stream is still draining: they
+// run their prologue (barrier init, TMEM allocation, descriptor prefetch, index math), then pdl_wait() blocks until the
+// previous grid has completed and its writes are visible.  Every kernel calls pdl_launch_dependents() first thing, so its
+// own successor can start the same way.  Both instructions are no-ops for a normally launched kernel.  NEKO_PDL=0 turns
+// the launch attribute off (plain stream order).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 

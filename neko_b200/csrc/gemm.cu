@@ -509,6 +509,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tmem_cols = 2u * BN;  // 256 or 512: a power of two >= 32
+  pdl_launch_dependents();             // the next kernel of the stream may start its own prologue as SMs free up
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -537,6 +538,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();                          // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   constexpr int TM = PAIR ? 2 * BM : BM;  // rows of C per work unit
   const int m_blocks = (p.M + TM - 1) / TM;
@@ -895,15 +897,18 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = as_stream(stream);
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, mc, mc2, mc3, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm pair)");
   } else {
     const int grid = (int)(units < sms ? units : sms);
-    gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma, mb, mc, mc2, mc3, p);
+    cudaError_t e = launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), smem, as_stream(stream), ma, mb, mc, mc2, mc3, p);
+    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm)");
   }
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return NEKO_OK;
