@@ -632,6 +632,10 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
   return NEKO_OK;
 }
 
+// tcgen05 forward (attention_tc.cu): 0 = ran, 1 = shape not covered, < 0 = error
+int attention_fwd_tc(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int dh, int out_f16,
+                     DropCfg drop, cudaStream_t st);
+
 }  // namespace neko
 
 extern "C" {
@@ -648,6 +652,10 @@ int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t
   bf16* o2 = reinterpret_cast<bf16*>(out2_bf16);
   cudaStream_t st = as_stream(stream);
   const DropCfg dc = drop_cfg(drop);
+  {  // tensor-core (tcgen05 / TMEM / TMA) path for head dims 32 and 64; the mma.sync kernels below are the fallback
+    const int rc_tc = attention_fwd_tc(x, first_valid, o, o2, lse, B, S, S_valid, H, dh, out_f16, dc, st);
+    if (rc_tc <= 0) return rc_tc;
+  }
 #define NEKO_ATT_FWD(DH_) (dc.seed ? launch_fwd<DH_, true>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, dc, st) \
                                    : launch_fwd<DH_, false>(x, first_valid, o, o2, lse, B, S, S_valid, H, out_f16, dc, st))
   switch (dh) {

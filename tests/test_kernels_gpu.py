@@ -225,7 +225,9 @@ def _attn_ref(qkv, first_valid, H, S_valid):
 
 @pytest.mark.parametrize("B,S,H,dh,S_valid", [(2, 64, 2, 32, 64), (3, 100, 3, 32, 100), (2, 240, 24, 32, 240), (2, 130, 1, 128, 130),
                                                (2, 96, 4, 16, 80), (2, 200, 2, 64, 200), (1, 494, 24, 32, 494)])
-def test_attention_fwd_bwd(ops, B, S, H, dh, S_valid):
+@pytest.mark.parametrize("tc", [0, 1])
+def test_attention_fwd_bwd(ops, monkeypatch, tc, B, S, H, dh, S_valid):
+    monkeypatch.setenv("NEKO_ATTN_TC", str(tc))   # 1: tcgen05 forward where the shape allows it (dh 32 with even H, dh 64)
     d = H * dh
     qkv = _rand((B, S, 3 * d), 21, 1.0, torch.bfloat16)
     fv = torch.tensor([0, 17, 70][:B], dtype=torch.int32).clamp(max=S_valid - 1).cuda()
@@ -450,9 +452,12 @@ def test_gemm_residual_dropout_and_layernorm_bwd_branch_mask(ops):
     assert (c_b - (dxb_ * mult).sum(0)).abs().max().item() < 2e-2 * max(1.0, float((dxb_ * mult).sum(0).abs().max()))
 
 
-@pytest.mark.parametrize("B,S,H,dh,S_valid", [(2, 200, 3, 32, 200), (2, 130, 2, 64, 120), (1, 64, 1, 128, 64), (3, 96, 2, 16, 96)])
-def test_attention_dropout_fwd_bwd(ops, B, S, H, dh, S_valid):
+@pytest.mark.parametrize("B,S,H,dh,S_valid", [(2, 200, 3, 32, 200), (2, 130, 2, 64, 120), (1, 64, 1, 128, 64), (3, 96, 2, 16, 96),
+                                               (2, 300, 4, 32, 300)])
+@pytest.mark.parametrize("tc", [0, 1])
+def test_attention_dropout_fwd_bwd(ops, monkeypatch, tc, B, S, H, dh, S_valid):
     from neko_b200._lib import Dropout
+    monkeypatch.setenv("NEKO_ATTN_TC", str(tc))
     d = H * dh
     dr = Dropout.make(_seed(31, 32), 5, 0.2)
     qkv = _rand((B, S, 3 * d), 11, 0.7, torch.bfloat16)
@@ -475,3 +480,35 @@ def test_attention_dropout_fwd_bwd(ops, B, S, H, dh, S_valid):
     g = qf.grad
     rel = ((dqkv.float() - g)[live].norm() / g[live].norm()).item()
     assert rel < 3e-2, rel
+
+
+@pytest.mark.parametrize("B,S,H,dh,S_valid,fvs", [(3, 512, 4, 32, 512, (0, 130, 300)), (2, 300, 2, 64, 260, (5, 129)),
+                                                   (3, 1024, 2, 32, 1024, (0, 255, 1000)), (2, 128, 2, 32, 128, (0, 127))])
+@pytest.mark.parametrize("tc", [1, 0])
+def test_attention_tensor_core_forward_long(ops, monkeypatch, tc, B, S, H, dh, S_valid, fvs):
+    """Both forward paths -- tcgen05/TMEM/TMA (attention_tc.cu, NEKO_ATTN_TC=1) and mma.sync (default) -- on several
+    128-key tiles, left padding beyond the first tile, right padding."""
+    monkeypatch.setenv("NEKO_ATTN_TC", str(tc))
+    d = H * dh
+    qkv = _rand((B, S, 3 * d), 23, 1.0, torch.bfloat16)
+    fv = torch.tensor(list(fvs), dtype=torch.int32).cuda()
+    o2 = torch.empty(B, S, d, device="cuda", dtype=torch.bfloat16)
+    out, lse = ops.attention_fwd(qkv, fv, H, S_valid, out_dtype=torch.float16, out2=o2)
+    ref, mask = _attn_ref(qkv.float(), fv, H, S_valid)
+    live = mask.bool()[:, :, None].expand(B, S, d)
+    assert ((out.float() - ref) * live).abs().max().item() < 0.03
+    assert ((o2.float() - ref) * live).abs().max().item() < 0.03
+    assert (out.float() * (~live)).abs().max().item() == 0.0
+    # log-sum-exp of the live rows against the fp32 scores
+    q, k, _ = (t.view(B, S, H, dh).transpose(1, 2) for t in qkv.float().split(d, dim=2))
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    idx = torch.arange(S, device="cuda")
+    ok = (idx[None, :] <= idx[:, None])[None, None] & (idx[None, None, None, :] >= fv[:, None, None, None])
+    ref_lse = torch.logsumexp(sc.masked_fill(~ok, float("-inf")), dim=-1)
+    lrow = mask.bool()[:, None, :].expand(B, H, S)
+    assert (lse - ref_lse)[lrow].abs().max().item() < 2e-2
+    assert torch.isinf(lse[~lrow]).all()
+    # and the mma.sync backward consumes it
+    dout = _rand((B, S, d), 24, 1.0, torch.bfloat16) * live
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, fv, H, S_valid)
+    assert torch.isfinite(dqkv.float()).all()
