@@ -270,7 +270,9 @@ def run_ours(args):
     sync = None
     if world > 1:
         dp.broadcast_parameters(model)
-        sync = dp.attach(model)
+        # static knowledge of the task mix, as a trainer has it from --text_prop / --caption_prop / --vqa_prop
+        no_text = not any(("text" in s and s["text"] is not None) for s in O.synth_batch(args.config, seed=0))
+        sync = dp.attach(model, no_text_tokens=no_text)
     host_batch = O.synth_batch(args.config, seed=1234 + rank)
     dev_batch = to_device(host_batch, dev)
     pin_batch = to_pinned(host_batch)

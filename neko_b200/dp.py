@@ -32,6 +32,9 @@ class GradSynchronizer:
         self._cuda = arena.is_cuda
         self._stream = torch.cuda.Stream(device=arena.device) if self._cuda else None
         self.launched: List[Tuple[int, int]] = []   # bucket log of the last step (tests)
+        # arena ranges the caller guarantees to be zero on EVERY rank (e.g. the text rows of embed_token when no task
+        # of the mix produces text tokens): averaging zeros is a no-op, so they are left out of the all-reduce
+        self.skip_ranges: List[Tuple[int, int]] = []
 
     # -- hook called by the backward engine -----------------------------------------------------------
     def on_range_ready(self, lo: int, hi: int):
@@ -48,10 +51,26 @@ class GradSynchronizer:
 
     def _flush(self):
         for lo, hi in self._pending:
-            # split oversized ranges so that the first chunk can start while later ones are still queued
-            for s in range(lo, hi, self.bucket_elems):
-                self._launch(s, min(hi, s + self.bucket_elems))
+            for a, b in self._minus_skipped(lo, hi):
+                # split oversized ranges so that the first chunk can start while later ones are still queued
+                for s in range(a, b, self.bucket_elems):
+                    self._launch(s, min(b, s + self.bucket_elems))
         self._pending = []
+
+    def _minus_skipped(self, lo: int, hi: int):
+        out = [(lo, hi)]
+        for slo, shi in self.skip_ranges:
+            nxt = []
+            for a, b in out:
+                if shi <= a or slo >= b:
+                    nxt.append((a, b))
+                else:
+                    if a < slo:
+                        nxt.append((a, slo))
+                    if shi < b:
+                        nxt.append((shi, b))
+            out = nxt
+        return out
 
     def _launch(self, lo: int, hi: int):
         view = self.arena[lo:hi]
@@ -94,9 +113,19 @@ class GradSynchronizer:
             self._pending = []
 
 
-def attach(policy, group=None, bucket_bytes: int = 64 << 20) -> GradSynchronizer:
-    """Wire a GradSynchronizer to a GatoPolicy: buckets fire from inside ``loss.backward()``."""
+def attach(policy, group=None, bucket_bytes: int = 64 << 20, no_text_tokens: bool = False) -> GradSynchronizer:
+    """Wire a GradSynchronizer to a GatoPolicy: buckets fire from inside ``loss.backward()``.
+
+    ``no_text_tokens``: the caller guarantees that no rank ever feeds text tokens (a task mix with
+    text_prop = caption_prop = vqa_prop = 0, trainer.py:134): rows [0, text_tokens) of ``embed_token`` -- 154 MB of the
+    last, non-overlappable bucket -- then have zero gradient everywhere and are left out of the all-reduce, like the
+    never-used ``transformer.wte``.  The result is identical to the dense all-reduce."""
     sync = GradSynchronizer(policy._grad_arena, group=group, bucket_bytes=bucket_bytes)
+    if no_text_tokens:
+        o = policy._offs["embed_token.weight"]
+        sync.skip_ranges.append((o, o + policy.text_tokens * policy.embed_dim))
+        w = policy._offs["transformer.wte.weight"]
+        sync.skip_ranges.append((w, w + policy._params["transformer.wte.weight"].numel()))
     policy.grad_ready_hook = sync.on_range_ready
     policy._grad_sync = sync
     return sync

@@ -141,6 +141,19 @@ with s2.no_sync():
 assert torch.equal(arena2, torch.ones(100) * (rank + 1))
 s2.on_range_ready(0, 100); s2.finish()
 assert torch.allclose(arena2, torch.ones(100) * 1.5)
+# skip ranges: parts of the arena that are zero on every rank by construction are left out of the collectives
+arena3 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+arena3[200:700] = 0.0
+s3 = GradSynchronizer(arena3, bucket_bytes=4 * 128)
+s3.skip_ranges += [(200, 700), (990, 1000)]
+s3.begin_step()
+s3.on_range_ready(0, 500); s3.on_range_ready(500, 1000); s3.finish()
+ref3 = torch.arange(1000, dtype=torch.float32) * 1.5
+ref3[200:700] = 0.0
+ref3[990:] = torch.arange(990, 1000, dtype=torch.float32) * (rank + 1)      # skipped: stays local
+assert torch.allclose(arena3, ref3)
+assert all(hi <= 200 or lo >= 700 for lo, hi in s3.launched) and all(hi <= 990 for lo, hi in s3.launched)
+assert sum(hi - lo for lo, hi in s3.launched) == 1000 - 500 - 10
 dist.destroy_process_group()
 print("ok", rank)
 """

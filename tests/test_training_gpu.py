@@ -1,0 +1,109 @@
+"""End-to-end optimisation steps on the GPU: Trainer + FusedAdamW (clip + AdamW over the flat arena, LR schedule) against
+torch.optim.AdamW driven by the CPU oracle's gradients on the same batches (train.py:127-136, trainer.py:176-188)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import gato_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Tok:
+    def __init__(self, n):
+        self.vocab_size = n
+
+
+class _Replay:
+    """Task stub that replays a fixed list of batches (kind 'control')."""
+    kind = "control"
+
+    def __init__(self, batches):
+        self.batches, self.i = batches, 0
+
+    def sample_batch(self, n, max_tokens=None):
+        b = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        return copy.deepcopy(b)
+
+
+def _batches(cfg, steps, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(steps):
+        out.append([dict(continuous_obs=torch.randn(6, 5, generator=g) * 3,
+                         continuous_actions=torch.randn(6, 2, generator=g).clamp(-1, 1)) for _ in range(3)])
+    return out
+
+
+@pytest.mark.parametrize("lean", [True, False])
+def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
+    from neko_b200.policy import GatoPolicy
+    from neko_b200.training.arguments import TrainingArgs
+    from neko_b200.training.trainer import FusedAdamW, Trainer, lr_at_step
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=64, text_tokens=120)
+    w = O.make_weights(cfg, seed=11)
+    m = GatoPolicy(device="cuda", embed_dim=64, layers=2, heads=2, dropout=0.0, resid_mid_channels=128, context_len=64,
+                   text_tokenizer=_Tok(120))
+    m.transformer.drop.p = 0.0
+    m.load_state_dict(w, strict=False)
+    m.materialize_logits = not lean
+    steps = 4
+    args = TrainingArgs()
+    args.batch_size, args.sequence_length = 3, 64
+    args.learning_rate, args.init_lr, args.min_factor = 1e-3, 1e-4, 10.0
+    args.warmup_steps, args.training_steps = 2, 8
+    args.grad_norm_clip, args.disable_grad_clip = 1.0, False
+    args.gradient_accumulation_steps = 1
+    args.text_prop = args.caption_prop = args.vqa_prop = 0.0
+    batches = _batches(cfg, steps)
+
+    class _OneSample(_Replay):
+        """Trainer draws control samples one at a time (trainer.py:211-247): hand out the batch sample by sample."""
+        def __init__(self, batches):
+            super().__init__([s for b in batches for s in b])
+
+        def sample_batch(self, n, max_tokens=None):
+            s = self.batches[self.i % len(self.batches)]
+            self.i += 1
+            return [copy.deepcopy(s)]
+
+    opt = FusedAdamW(m, lr=args.learning_rate, betas=(args.beta_1, args.beta_2), eps=args.adam_eps, weight_decay=args.weight_decay)
+    tr = Trainer(m, opt, [_OneSample(batches)], args)
+    losses = [l for l, _ in tr.train(steps)]
+
+    # reference: oracle forward/backward on CPU + torch AdamW with the same schedule and clipping
+    for t in w.values():
+        t.requires_grad_(True)
+    used = [t for n, t in w.items() if n != "transformer.wte.weight" and not n.startswith("image_embedding.")]
+    ropt = torch.optim.AdamW(list(w.values()), lr=args.learning_rate, betas=(args.beta_1, args.beta_2), eps=args.adam_eps,
+                             weight_decay=args.weight_decay)
+    rlosses = []
+    for s in range(steps):
+        lr = lr_at_step(s, warmup_steps=args.warmup_steps, training_steps=args.training_steps, base_lr=args.learning_rate,
+                        init_lr=args.init_lr, min_lr=args.learning_rate / args.min_factor, cosine_decay=True)
+        for gI in ropt.param_groups:
+            gI["lr"] = lr
+        out = O.forward(w, batches[s], cfg, compute_loss=True, training=True)
+        ropt.zero_grad()
+        out.loss.backward()
+        for t in w.values():                      # parameters without gradient still decay in the fused arena update
+            if t.grad is None:
+                t.grad = torch.zeros_like(t)
+        torch.nn.utils.clip_grad_norm_(list(w.values()), args.grad_norm_clip)
+        ropt.step()
+        rlosses.append(float(out.loss))
+    assert len(used) > 10
+    for a, b in zip(losses, rlosses):
+        assert abs(a - b) <= 2e-3 * abs(b), (losses, rlosses)
+    assert losses[-1] < losses[0]
+    # parameters after 4 AdamW steps: updates are O(lr) per step whatever the gradient scale, so compare in units of lr
+    sd = m.state_dict()
+    worst = 0.0
+    for n, t in w.items():
+        if n == "transformer.wte.weight":
+            continue
+        diff = (sd[n].detach().cpu() - t.detach()).abs()
+        worst = max(worst, float(diff.mean()) / args.learning_rate)
+    assert worst < 0.5, worst

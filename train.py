@@ -42,7 +42,8 @@ def main():
     sync = None
     if world > 1:
         dp.broadcast_parameters(model)
-        sync = dp.attach(model)
+        # a mix without text / caption / VQA never touches the text rows of embed_token on any rank (trainer.py:134)
+        sync = dp.attach(model, no_text_tokens=(args.text_prop + args.caption_prop + args.vqa_prop) == 0)
     if rank == 0:
         print("Trainable Parameters:", "{}M".format(sum(p.numel() for p in model.parameters()) / 1e6))
     opt = FusedAdamW(model, lr=args.learning_rate, betas=(args.beta_1, args.beta_2), eps=args.adam_eps, weight_decay=args.weight_decay)
