@@ -180,6 +180,11 @@ int neko_gemm(const neko_gemm_desc* host_desc, void* stream);
 int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t* out,
                        uint16_t* out2_bf16 /* nullable second copy */, float* lse, int B, int S, int S_valid,
                        int H, int dh, int out_f16, const neko_dropout* drop, void* stream);
+/* Single-query attention against a key/value cache (KV-cached decode for the predict_* loops, gato_policy.py:452-476 --
+ * the reference re-runs the whole context per generated token).  q bf16 [H*dh] (the new position's query), k_cache /
+ * v_cache bf16 [len, H*dh] (all visible keys incl. the new one), out 16-bit [H*dh]. */
+int neko_attention_decode(const uint16_t* q, const uint16_t* k_cache, const uint16_t* v_cache, int len, int H, int dh,
+                          uint16_t* out, int out_f16, void* stream);
 /* dqkv bf16 [B,S,3*H*dh]; delta fp32 [B,H,S] is caller-provided scratch. */
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse,
                        const int32_t* first_valid, uint16_t* dqkv, float* delta, int B, int S, int S_valid,

@@ -632,6 +632,61 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
   return NEKO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-query attention against a key/value cache (KV-cached decode of the predict_* loops, gato_policy.py:452-476):
+// one CTA per head; scores of all cached keys in shared memory, fp32 softmax, weighted sum of V.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                                                          int len, int d, int dh, float scale, uint16_t* __restrict__ out, int out_f16) {
+  extern __shared__ float dec_s[];          // [len] scores, then [128] reduction scratch
+  float* red = dec_s + len;
+  const int h = blockIdx.x, tid = threadIdx.x;
+  const bf16* qh = q + h * dh;
+  // scores
+  float lmax = -INFINITY;
+  for (int j = tid; j < len; j += 128) {
+    const bf16* kr = kc + (size_t)j * d + h * dh;
+    float acc = 0.f;
+    for (int c = 0; c < dh; c += 2) {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qh + c));
+      const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kr + c));
+      acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+    }
+    acc *= scale;
+    dec_s[j] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  lmax = warp_max(lmax);
+  if ((tid & 31) == 0) red[tid >> 5] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = tid; j < len; j += 128) {
+    const float p = __expf(dec_s[j] - mx);
+    dec_s[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if ((tid & 31) == 0) red[tid >> 5] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+  __syncthreads();
+  // out[c] = sum_j p_j v[j][c]: thread = (dimension c, key slice)
+  const int slices = 128 / dh > 0 ? 128 / dh : 1;
+  const int c = tid % dh, sl = tid / dh;
+  float acc = 0.f;
+  if (sl < slices)
+    for (int j = sl; j < len; j += slices) acc = fmaf(dec_s[j], __bfloat162float(vc[(size_t)j * d + h * dh + c]), acc);
+  red[tid] = (sl < slices) ? acc : 0.f;
+  __syncthreads();
+  if (tid < dh) {
+    float t = 0.f;
+    for (int s2 = 0; s2 < slices; ++s2) t += red[s2 * dh + tid];
+    out[h * dh + tid] = cvt_16(t * inv, out_f16 != 0);
+  }
+}
+
 // tcgen05 forward (attention_tc.cu): 0 = ran, 1 = shape not covered, < 0 = error
 int attention_fwd_tc(const bf16* qkv, const int32_t* fv, bf16* out, bf16* out2, float* lse, int B, int S, int S_valid, int H, int dh, int out_f16,
                      DropCfg drop, cudaStream_t st);
@@ -666,6 +721,19 @@ int neko_attention_fwd(const uint16_t* qkv, const int32_t* first_valid, uint16_t
     default: set_error("attention: head dim %d not supported (16, 32, 64, 128)", dh); return NEKO_EINVAL;
   }
 #undef NEKO_ATT_FWD
+}
+
+int neko_attention_decode(const uint16_t* q, const uint16_t* k_cache, const uint16_t* v_cache, int len, int H, int dh, uint16_t* out,
+                          int out_f16, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(q && k_cache && v_cache && out, "attention_decode: null pointer");
+  NEKO_REQUIRE(len > 0 && len <= 8192 && H > 0 && dh > 0 && dh <= 128 && dh % 2 == 0 && 128 % dh == 0, "attention_decode: bad sizes (len=%d dh=%d)", len, dh);
+  const size_t smem = (size_t)(len + 128) * sizeof(float);
+  attn_decode_kernel<<<H, 128, smem, as_stream(stream)>>>(reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k_cache),
+                                                         reinterpret_cast<const bf16*>(v_cache), len, H * dh, dh, 1.0f / sqrtf((float)dh), out,
+                                                         out_f16);
+  NEKO_LAUNCH_CHECK("attn_decode_kernel");
+  return NEKO_OK;
 }
 
 int neko_attention_bwd(const uint16_t* qkv, const uint16_t* out, const uint16_t* dout, const float* lse, const int32_t* first_valid,

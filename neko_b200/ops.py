@@ -156,6 +156,14 @@ def attention_fwd(qkv: torch.Tensor, first_valid: torch.Tensor, H: int, S_valid:
     return out, lse
 
 
+def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, length: int, H: int, out: torch.Tensor):
+    """One new query against `length` cached keys / values (bf16 [>=length, d])."""
+    d = q.numel()
+    check(load().neko_attention_decode(_p(q), _p(k_cache), _p(v_cache), C.c_int(length), C.c_int(H), C.c_int(d // H), _p(out),
+                                       C.c_int(int(out.dtype == torch.float16)), stream_ptr()), "neko_attention_decode")
+    return out
+
+
 def attention_bwd(qkv, out, dout, lse, first_valid, H: int, S_valid: Optional[int] = None, dqkv=None, delta=None, drop=None):
     B, S, three_d = qkv.shape
     dh = three_d // 3 // H

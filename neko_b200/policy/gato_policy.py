@@ -160,6 +160,16 @@ class _State:
     pass
 
 
+class _KVCache:
+    """Keys / values of one sequence for the KV-cached predict_* loops: bf16 [layers, context_len, d] each."""
+
+    def __init__(self, layers: int, ctx: int, d: int, device):
+        self.k = torch.empty(layers, ctx, d, dtype=torch.bfloat16, device=device)
+        self.v = torch.empty(layers, ctx, d, dtype=torch.bfloat16, device=device)
+        self.len = 0            # positions held
+        self.decoding = False   # False: prefill (fill from a full forward); True: one new position per call
+
+
 class GatoPolicy(nn.Module):
     def __init__(
         self,
@@ -267,6 +277,7 @@ class GatoPolicy(nn.Module):
         self._gscale_buf = torch.ones((), dtype=torch.float32, device=dev)
         self.launches = 0
         self._drop_gen = None
+        self.use_kv_cache = True        # predict_* loops: key/value cache instead of re-running the context per token
         self._build_arena()
 
     # ------------------------------------------------------------------------------------------
@@ -485,13 +496,35 @@ class GatoPolicy(nn.Module):
         """Autoregressive continuation on caller-owned embeddings: logits of the last position restricted to ids
         [lo, hi], pick, embed the pick, append, trim to context_len (gato_policy.py:452-476 and :586-605)."""
         rows, picked = [], []
+        # KV cache (SURVEY 8(f)2): the reference re-runs the whole context for every generated token; here the first call
+        # fills a key/value cache and later calls push ONE position through the decoder.  Used for a single unpadded
+        # sequence in eval mode while the context still fits (a sliding window changes what the cached positions would
+        # have seen, so from then on the context is recomputed like the reference does).
+        use_kv = (self.use_kv_cache and not self.training and token_embeddings.shape[0] == 1
+                  and bool((token_masks == 1).all()))
+        cache = None
         for _ in range(n_tokens):
-            logits, _ = self.forward(token_embeddings=token_embeddings, token_masks=token_masks, token_target_masks=None, tokens=None)
-            row = logits[0, -1, lo:hi + 1]
+            S_now = token_embeddings.shape[1]
+            if use_kv and S_now <= self.context_len:
+                if cache is not None and cache.len == S_now - 1:
+                    cache.decoding = True
+                    hf = self._decode_hidden(token_embeddings[:, -1:, :], None, kv=cache)          # [1, d]
+                else:
+                    cache = _KVCache(self.layers, self.context_len, self.embed_dim, self.device)
+                    hf = self._decode_hidden(token_embeddings, token_masks, kv=cache)[-1:]          # last position
+                cache.len = S_now
+                full = self._head(hf.contiguous(), 1)
+                row = full[0, lo:hi + 1]
+            else:
+                cache = None
+                logits, _ = self.forward(token_embeddings=token_embeddings, token_masks=token_masks, token_target_masks=None, tokens=None)
+                row = logits[0, -1, lo:hi + 1]
             rows.append(row)
             tok = self._pick(row, deterministic) + lo
             token_masks = torch.cat([token_masks, torch.ones(token_masks.shape[0], 1, device=self.device)], dim=1)
             token_embeddings = torch.cat([token_embeddings, self.embed_token(tok).reshape(1, 1, -1)], dim=1)
+            if token_embeddings.shape[1] > self.context_len:   # the window slides: cached positions are stale
+                cache = None
             token_embeddings = token_embeddings[:, -self.context_len:, :]
             token_masks = token_masks[:, -self.context_len:]
             picked.append(tok)
@@ -800,8 +833,18 @@ class GatoPolicy(nn.Module):
             ops.gemm(ln1, self._wview(pre + "attn.c_attn.weight"), b_mn=True, epilogue=ops.EPI_BF16, out=qkv, bias=blk.attn.c_attn.bias)
             att, att_b = pair("att", tag, (N, d))
             lse = self._buf("lse" + tag, (B, H, W), torch.float32)
-            ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse,
-                              out2=att_b.view(B, W, d) if dual else None, drop=self._drop_site(st, 4 * i + 1, blk.attn.attn_dropout.p))
+            kv = getattr(st, "kv", None)
+            if kv is not None and kv.decoding:
+                # KV-cached decode: N == 1; append this position's key / value, attend over the cache
+                kv.k[i, kv.len].copy_(qkv[0, d:2 * d])
+                kv.v[i, kv.len].copy_(qkv[0, 2 * d:])
+                ops.attention_decode(qkv[0, :d], kv.k[i], kv.v[i], kv.len + 1, H, att.view(d))
+            else:
+                ops.attention_fwd(qkv.view(B, W, 3 * d), first_valid, H, S_valid, att.view(B, W, d), lse,
+                                  out2=att_b.view(B, W, d) if dual else None, drop=self._drop_site(st, 4 * i + 1, blk.attn.attn_dropout.p))
+                if kv is not None:   # prefill: keep the keys / values of the context
+                    kv.k[i, :W].copy_(qkv[:W, d:2 * d])
+                    kv.v[i, :W].copy_(qkv[:W, 2 * d:])
             x1 = self._buf(f"x.{2 * i + 1}" if keep else "x.b", (N, d), torch.float32)
             ops.gemm(att, self._wview(pre + "attn.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x1, aux=x,
                      bias=blk.attn.c_proj.bias, drop=self._drop_site(st, 4 * i + 2, blk.attn.resid_dropout.p))
@@ -852,9 +895,10 @@ class GatoPolicy(nn.Module):
         B, S, d = emb.shape
         return self._decode_hidden(emb, mask).view(B, S, d).to(torch.float32)
 
-    def _decode_hidden(self, emb: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    def _decode_hidden(self, emb: torch.Tensor, mask: Optional[torch.Tensor], kv=None) -> torch.Tensor:
         """Decoder on caller-supplied embeddings (the kwargs path used by predict_*, gato_policy.py:160-169);
-        returns ln_f output as the bf16 [B*S, d] head operand."""
+        returns ln_f output as the bf16 [B*S, d] head operand.  ``kv``: optional _KVCache to fill (prefill) or to decode
+        one new position against."""
         with torch.no_grad():
             self._refresh_bf16()
             B, S, d = emb.shape
@@ -865,6 +909,7 @@ class GatoPolicy(nn.Module):
             else:  # first valid key per sample; right padding is never visible to a valid (causal) query
                 fv = (mask.to(self.device).cumsum(1) == 0).sum(1).to(torch.int32)
             st = _State()
+            st.kv = kv
             seed = self._next_drop_seed()
             st.drop_seed = torch.from_numpy(seed).to(self.device) if seed is not None else None
             return self._decoder(st, x, B, S, S, fv, keep=False)

@@ -447,3 +447,42 @@ def test_predict_response_runs_on_image_embeddings():
     ref = O.forward(w, batch, cfg, compute_loss=False)
     row = ref.logits[0, -2, :cfg.text_tokens]     # position of the last prompt token (the separator follows it)
     assert (logits[0].cpu() - row).abs().max().item() <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("case", ["text", "control", "overflow"])
+def test_kv_cached_generation_matches_full_recompute(case):
+    """the KV-cached decode (one position per step) against re-running the whole context per token (what the
+    reference does and what use_kv_cache=False does), incl. the fallback once the context window starts to slide."""
+    import types
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=32 if case == "overflow" else 64, text_tokens=200)
+    w = O.make_weights(cfg, seed=21)
+    m = make_policy(cfg, w)
+    rs = np.random.RandomState(4)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+
+    def run(use_kv):
+        m.use_kv_cache = use_kv
+        if case == "control":
+            obs, act = f32(rs0.standard_normal((4, 5)) * 2), f32(np.clip(rs0.standard_normal((4, 3)), -1, 1))
+            task = types.SimpleNamespace(action_type=type("Box", (), {}), action_tokens=3, env=None)
+            a = m.predict_control(dict(continuous_obs=obs.cuda(), continuous_actions=act.cuda()), task, deterministic=True)
+            return a.float().cpu(), None
+        n_prompt, n_new = (28, 8) if case == "overflow" else (11, 7)
+        prompt = rs0.randint(0, 200, (n_prompt,)).tolist()
+        logits, toks = m.predict_text(dict(text=prompt), max_length=n_new, deterministic=True)
+        return logits.float().cpu(), [int(t) for t in toks]
+
+    rs0 = np.random.RandomState(4)
+    a_kv, t_kv = run(True)
+    rs0 = np.random.RandomState(4)
+    a_full, t_full = run(False)
+    if case == "control":
+        assert (a_kv - a_full).abs().max().item() <= 2.0 / cfg.continuous_tokens * 4
+        return
+    # same greedy continuation as long as the argmax margin is unambiguous; logits of every compared step within tolerance
+    for i in range(len(t_full)):
+        assert (a_kv[i] - a_full[i]).abs().max().item() <= LOGIT_TOL, i
+        top = torch.topk(a_full[i], 2).values
+        if float(top[0] - top[1]) <= 4 * LOGIT_TOL:
+            break
+        assert t_kv[i] == t_full[i], i

@@ -93,7 +93,7 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
                 t.grad = torch.zeros_like(t)
         torch.nn.utils.clip_grad_norm_(list(w.values()), args.grad_norm_clip)
         ropt.step()
-        rlosses.append(float(out.loss))
+        rlosses.append(float(out.loss.detach()))
     assert len(used) > 10
     for a, b in zip(losses, rlosses):
         assert abs(a - b) <= 2e-3 * abs(b), (losses, rlosses)
