@@ -331,6 +331,8 @@ class GatoPolicy(nn.Module):
         self._offs = offs
         self._order = order
         self._params = params
+        self._gview_cache = {}
+        self._wview_cache = {}
         # gradient ranges that must start from zero each step (everything except the matrices a single non-split
         # or self-zeroing wgrad GEMM overwrites)
         overwritten = {"predict_token.weight"} | {f"transformer.h.{i}.{m}.weight" for i in range(self.layers)
@@ -359,18 +361,30 @@ class GatoPolicy(nn.Module):
                 break
 
     def _gview(self, name: str) -> torch.Tensor:
-        p = self._params[name]
-        o = self._offs[name]
-        return self._grad_arena[o:o + p.numel()].view(p.shape)
+        """Gradient of a parameter as a view of the gradient arena (cached: the host path creates ~100 of them per step)."""
+        v = self._gview_cache.get(name)
+        if v is None or v.data_ptr() != self._grad_arena.data_ptr() + 4 * self._offs[name]:
+            p = self._params[name]
+            o = self._offs[name]
+            v = self._grad_arena[o:o + p.numel()].view(p.shape)
+            self._gview_cache[name] = v
+        return v
 
     def _wview(self, name: str, rows: Optional[int] = None, bwd: bool = False) -> torch.Tensor:
-        """16-bit operand copy of a weight: forward format, or bf16 for the backward GEMMs."""
+        """16-bit operand copy of a weight: forward format, or bf16 for the backward GEMMs (views are cached)."""
         arena = self._wbf_arena if bwd else self._w16_arena
+        key = (name, rows, bwd)
+        hit = self._wview_cache.get(key)
+        if hit is not None and hit[0] is arena:
+            return hit[1]
         p = self._params[name]
         o = self._offs[name]
         if rows is not None:
-            return arena[o:o + rows * p.shape[1]].view(rows, p.shape[1])
-        return arena[o:o + p.numel()].view(p.shape)
+            v = arena[o:o + rows * p.shape[1]].view(rows, p.shape[1])
+        else:
+            v = arena[o:o + p.numel()].view(p.shape)
+        self._wview_cache[key] = (arena, v)
+        return v
 
     def _refresh_bf16(self, force: bool = False):
         vers = None if force else tuple(p._version for p in self._params.values())

@@ -51,10 +51,30 @@ def _is_present(d: dict, k: str) -> bool:
     return k in d and d[k] is not None
 
 
+_SEL_CACHE: dict = {}   # (T, n_patches, n_text, n_obs, tokens/timestep) -> local loss-row offsets (targets at s+1)
+
+
+def _loss_sel(T: int, n_patches: int, n_text: int, n_obs: int, tpt: int) -> np.ndarray:
+    """Local positions s in [0, T*tpt - 1) whose NEXT token is a target (text or action; gato_policy.py:362-369,174-180)."""
+    key = (T, n_patches, n_text, n_obs, tpt)
+    sel = _SEL_CACHE.get(key)
+    if sel is None:
+        pat = np.zeros(tpt, dtype=np.uint8)
+        pat[n_patches:n_patches + n_text] = 1
+        pat[n_obs + 1:] = 1
+        sel = np.nonzero(np.tile(pat, T)[1:])[0].astype(np.int32)
+        if len(_SEL_CACHE) > 4096:
+            _SEL_CACHE.clear()
+        _SEL_CACHE[key] = sel
+    return sel
+
+
 def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad_seq: bool) -> BatchPlan:
+    """Host half of tokenize_input_dicts (gato_policy.py:195-432): shapes only -- one 16-int descriptor per sample, the
+    flat value lists, left-padding offsets and the loss rows.  Runs once per step on the host, so the per-sample work is
+    kept to plain Python ints and list appends; descriptors become one int32 array at the end."""
     B = len(inputs)
     assert B > 0, "empty batch"
-    descs = (SampleDesc * B)()
     fvals: List[torch.Tensor] = []
     ivals: List[torch.Tensor] = []
     n_f = n_i = 0
@@ -62,134 +82,143 @@ def build_plan(inputs: Sequence[dict], *, patch_size: int, context_len: int, pad
     pre_patch: List[Tuple[int, torch.Tensor]] = []
     pre_samples = []
     n_patch_rows = 0
-    lengths = []
-    tgt_patterns = []
-
-    def add_f(t: torch.Tensor) -> int:
-        nonlocal n_f
-        off = n_f
-        t = t.detach()
-        if t.dtype != torch.float32:
-            t = t.to(torch.float32)
-        fvals.append(t.reshape(-1))
-        n_f += t.numel()
-        return off
-
-    def add_i(t) -> int:
-        nonlocal n_i
-        off = n_i
-        if not isinstance(t, torch.Tensor):
-            t = torch.as_tensor(t)
-        t = t.detach()
-        if t.dtype != torch.int32:
-            t = t.to(torch.int32)
-        ivals.append(t.reshape(-1))
-        n_i += t.numel()
-        return off
+    # descriptor columns, in the order of neko_sample_desc
+    rows16 = []
+    f32, i32 = torch.float32, torch.int32
 
     for b, s in enumerate(inputs):
-        d = descs[b]
-        T: Optional[int] = None
-
-        def check_T(n: int):
-            nonlocal T
-            if T is None:
-                T = n
-            else:
-                assert T == n, "number of timesteps must be the same for all modalities"
-
-        if _is_present(s, "text"):
-            txt = s["text"]
+        T = -1
+        n_patches = n_text = n_cobs = n_dobs = n_cact = n_dact = 0
+        text_off = cobs_off = dobs_off = cact_off = dact_off = 0
+        get = s.get
+        txt = get("text")
+        if txt is not None:
             if isinstance(txt, list):
-                # torch.Tensor(list) -> fp32 -> long in the reference (gato_policy.py:266-273)
-                txt = torch.tensor(txt, dtype=torch.float32).unsqueeze(0)
+                # torch.Tensor(list) -> fp32 -> long in the reference (gato_policy.py:266-273); numpy parses the list faster
+                txt = torch.from_numpy(np.asarray(txt, dtype=np.float32).astype(np.int32)).unsqueeze(0)
             elif txt.dim() == 1:
                 txt = txt.unsqueeze(0)
             T = int(txt.shape[0])
-            d.n_text = int(txt.shape[1])
-            d.text_off = add_i(txt.long())
-        if _is_present(s, "images") or _is_present(s, "image_embeddings"):
-            if _is_present(s, "image_embeddings"):
-                emb = s["image_embeddings"]
+            n_text = int(txt.shape[1])
+            text_off = n_i
+            t = txt.detach()
+            if t.dtype != i32:
+                t = t.long().to(i32)
+            ivals.append(t.reshape(-1))
+            n_i += t.numel()
+        emb = get("image_embeddings")
+        im = get("images") if emb is None else None
+        if emb is not None or im is not None:
+            if emb is not None:
                 n_img, n_p = int(emb.shape[0]), int(emb.shape[1])
                 pre_samples.append((b, emb, n_img * n_p))
             else:
-                im = s["images"]
                 assert im.dim() == 4 and im.shape[1] == 3, "images must be [T,3,H,W]"
                 h, w = int(im.shape[2]), int(im.shape[3])
                 assert h % patch_size == 0 and w % patch_size == 0, "Image dimensions must be divisible by patch size"
                 n_img, n_p = int(im.shape[0]), (h // patch_size) * (w // patch_size)
                 is_u8 = im.dtype == torch.uint8
-                if not is_u8 and im.dtype != torch.float32:
-                    im = im.to(torch.float32)
-                grp = next((g for g in groups if g.height == h and g.width == w and g.is_u8 == is_u8), None)
+                if not is_u8 and im.dtype != f32:
+                    im = im.to(f32)
+                grp = None
+                for g in groups:
+                    if g.height == h and g.width == w and g.is_u8 == is_u8:
+                        grp = g
+                        break
                 if grp is None:
                     grp = ImageGroup(h, w, is_u8)
                     groups.append(grp)
                 grp.tensors.append(im)
                 grp.sample_idx.append(b)
                 grp.n_frames += n_img
-            check_T(n_img)
-            d.n_patches = n_p
-        if _is_present(s, "continuous_obs"):
-            t = s["continuous_obs"]
-            check_T(int(t.shape[0]))
-            d.n_cobs = int(t.shape[1])
-            d.cobs_off = add_f(t)
-        if _is_present(s, "discrete_obs"):
-            t = s["discrete_obs"]
-            check_T(int(t.shape[0]))
-            d.n_dobs = int(t.shape[1])
-            d.dobs_off = add_i(t)
-        if _is_present(s, "continuous_actions"):
-            t = s["continuous_actions"]
-            check_T(int(t.shape[0]))
-            d.n_cact = int(t.shape[1])
-            d.cact_off = add_f(t)
-        if _is_present(s, "discrete_actions"):
-            t = s["discrete_actions"]
-            check_T(int(t.shape[0]))
-            d.n_dact = int(t.shape[1])
-            d.dact_off = add_i(t)
-        assert T is not None, "sample has no modality"
-        d.n_timesteps = T
-        n_obs = d.n_patches + d.n_text + d.n_cobs + d.n_dobs
-        tpt = n_obs + 1 + d.n_cact + d.n_dact
-        lengths.append(T * tpt)
-        # per-timestep target pattern (gato_policy.py:362-369): text and actions are targets
-        pat = np.zeros(tpt, dtype=np.uint8)
-        pat[d.n_patches:d.n_patches + d.n_text] = 1
-        pat[n_obs + 1:] = 1
-        tgt_patterns.append(np.tile(pat, T))
+            assert T < 0 or T == n_img, "number of timesteps must be the same for all modalities"
+            T = n_img
+            n_patches = n_p
+        t = get("continuous_obs")
+        if t is not None:
+            n = int(t.shape[0])
+            assert T < 0 or T == n, "number of timesteps must be the same for all modalities"
+            T = n
+            n_cobs = int(t.shape[1])
+            cobs_off = n_f
+            if t.requires_grad:
+                t = t.detach()
+            if t.dtype != f32:
+                t = t.to(f32)
+            fvals.append(t.reshape(-1))
+            n_f += n * n_cobs
+        t = get("discrete_obs")
+        if t is not None:
+            n = int(t.shape[0])
+            assert T < 0 or T == n, "number of timesteps must be the same for all modalities"
+            T = n
+            n_dobs = int(t.shape[1])
+            dobs_off = n_i
+            if not isinstance(t, torch.Tensor):
+                t = torch.as_tensor(t)
+            if t.dtype != i32:
+                t = t.to(i32)
+            ivals.append(t.reshape(-1))
+            n_i += n * n_dobs
+        t = get("continuous_actions")
+        if t is not None:
+            n = int(t.shape[0])
+            assert T < 0 or T == n, "number of timesteps must be the same for all modalities"
+            T = n
+            n_cact = int(t.shape[1])
+            cact_off = n_f
+            if t.requires_grad:
+                t = t.detach()
+            if t.dtype != f32:
+                t = t.to(f32)
+            fvals.append(t.reshape(-1))
+            n_f += n * n_cact
+        t = get("discrete_actions")
+        if t is not None:
+            n = int(t.shape[0])
+            assert T < 0 or T == n, "number of timesteps must be the same for all modalities"
+            T = n
+            n_dact = int(t.shape[1])
+            dact_off = n_i
+            if not isinstance(t, torch.Tensor):
+                t = torch.as_tensor(t)
+            if t.dtype != i32:
+                t = t.to(i32)
+            ivals.append(t.reshape(-1))
+            n_i += n * n_dact
+        assert T >= 0, "sample has no modality"
+        rows16.append([T, n_patches, n_text, n_cobs, n_dobs, n_cact, n_dact, 0,
+                       text_off, cobs_off, dobs_off, cact_off, dact_off, 0, 0, 0])
 
+    desc = np.array(rows16, dtype=np.int32)                 # [B, 16] == neko_sample_desc[B]
     # patch rows: one contiguous range per image group (one kernel launch each), then caller-supplied embeddings
     for g in groups:
         n_p = (g.height // patch_size) * (g.width // patch_size)
         for k, b in enumerate(g.sample_idx):
             g.patch_off.append(n_patch_rows)
-            descs[b].patch_off = n_patch_rows
+            desc[b, 13] = n_patch_rows
             n_patch_rows += int(g.tensors[k].shape[0]) * n_p
     for b, emb, n in pre_samples:
         pre_patch.append((n_patch_rows, emb))
-        descs[b].patch_off = n_patch_rows
+        desc[b, 13] = n_patch_rows
         n_patch_rows += n
 
-    S = max(lengths)
+    n_obs = desc[:, 1] + desc[:, 2] + desc[:, 3] + desc[:, 4]
+    tpt = n_obs + 1 + desc[:, 5] + desc[:, 6]
+    lengths = desc[:, 0] * tpt
+    S = int(lengths.max())
     width = context_len if (pad_seq and context_len > S) else S
-    first_valid = np.zeros(B, dtype=np.int32)
+    first_valid = (S - lengths).astype(np.int32)
+    desc[:, 7] = first_valid
     rows = []
     for b in range(B):
-        off = S - lengths[b]
-        descs[b].seq_off = off
-        first_valid[b] = off
         # loss row s: token s valid (s >= off) and target mask at s+1 set, s+1 < S
-        tgt = tgt_patterns[b]
-        sel = np.nonzero(tgt[1:])[0]           # local source positions 0..len-2
-        rows.append((b * width + off + sel).astype(np.int32))
-    loss_rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int32)
-    raw = np.frombuffer(C.string_at(C.addressof(descs), C.sizeof(descs)), dtype=np.uint8).copy()
+        sel = _loss_sel(int(desc[b, 0]), int(desc[b, 1]), int(desc[b, 2]), int(n_obs[b]), int(tpt[b]))
+        rows.append(sel + (b * width + int(first_valid[b])))
+    loss_rows = np.concatenate(rows).astype(np.int32, copy=False) if rows else np.zeros(0, dtype=np.int32)
+    raw = desc.view(np.uint8).reshape(-1)
     return BatchPlan(B=B, seq_len=S, width=width, descs=raw, fvals=fvals, ivals=ivals, n_f=n_f, n_i=n_i,
-                     first_valid=first_valid, loss_rows=loss_rows, n_valid_tokens=int(sum(lengths)),
+                     first_valid=first_valid, loss_rows=loss_rows, n_valid_tokens=int(lengths.sum()),
                      image_groups=groups, n_patch_rows=n_patch_rows, precomputed_patch=pre_patch)
 
 
