@@ -317,6 +317,104 @@ __global__ void __launch_bounds__(512) layernorm_bwd_staged_kernel(const bf16* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward, warp-per-row variant (default for d = 128 * NV, NV <= 8).  A warp owns whole rows: the two row statistics
+// need one shuffle reduction per ROW (the column-owner kernels above pay a block-wide reduction per 4 rows: ~1200
+// warp-instructions per row, issue-bound at 25 % -- profiles/r01_ncu_ln_bwd.txt), every lane keeps its 4*NV columns of
+// dgamma / dbeta / colsum in registers across all rows of the warp, and the CTA folds its warps' partials through shared
+// memory (warp after warp, no atomics) before ONE global atomicAdd per column.  ~200 warp-instructions per row.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256, 1) layernorm_bwd_rows_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, float* __restrict__ dx_resid,
+                                                                    bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float* __restrict__ dx_colsum, int N, int d,
+                                                                    DropCfg drop) {
+  extern __shared__ __align__(16) float lnr_s[];      // gamma [d] | acc [3][d]
+  float* sg = lnr_s;
+  float* sacc = lnr_s + d;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { sg[i] = gamma[i]; sacc[i] = 0.f; sacc[d + i] = 0.f; sacc[2 * d + i] = 0.f; }
+  __syncthreads();
+  float4 ag[NV], ab[NV], ac[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) ag[k] = ab[k] = ac[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_d = 1.0f / (float)d;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
+  const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
+  for (int row = gw; row < N; row += tw) {
+    const size_t off = (size_t)row * d;
+    const float4* x4 = reinterpret_cast<const float4*>(x + off);
+    const uint2* d2 = reinterpret_cast<const uint2*>(dy + off);
+    float4* r4 = reinterpret_cast<float4*>(dx_resid + off);
+    float4 xv[NV], rv[NV];
+    uint2 dv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { xv[k] = x4[lane + 32 * k]; dv[k] = d2[lane + 32 * k]; rv[k] = r4[lane + 32 * k]; }
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * (lane + 32 * k));
+      const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
+      // xv <- xhat ; keep dy * gamma in place of rv's partner via recomputation below
+      xv[k] = make_float4((xv[k].x - mu) * rs, (xv[k].y - mu) * rs, (xv[k].z - mu) * rs, (xv[k].w - mu) * rs);
+      const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * xv[k].x + g1 * xv[k].y) + (g2 * xv[k].z + g3 * xv[k].w);
+      ab[k].x += d01.x; ab[k].y += d01.y; ab[k].z += d23.x; ab[k].w += d23.y;
+      ag[k].x += d01.x * xv[k].x; ag[k].y += d01.y * xv[k].y; ag[k].z += d23.x * xv[k].z; ag[k].w += d23.y * xv[k].w;
+    }
+    const float m1 = warp_sum(s1) * inv_d, m2 = warp_sum(s2) * inv_d;
+    uint32_t rk = 0u;
+    if (drop.seed) rk = drop_rowkey(dkey, (uint32_t)row);
+    uint2* b2 = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + off) : nullptr;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * (lane + 32 * k));
+      const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
+      float4 o = rv[k];
+      o.x += rs * (d01.x * g.x - m1 - xv[k].x * m2);
+      o.y += rs * (d01.y * g.y - m1 - xv[k].y * m2);
+      o.z += rs * (d23.x * g.z - m1 - xv[k].z * m2);
+      o.w += rs * (d23.y * g.w - m1 - xv[k].w * m2);
+      r4[lane + 32 * k] = o;
+      if (drop.seed) {  // gradient entering the dropped-out residual branch: mask * scale * dx
+        float m0, m1_, m2_, m3;
+        drop_pair(rk, 2u * (lane + 32 * k), drop.thr16, drop.scale, m0, m1_);
+        drop_pair(rk, 2u * (lane + 32 * k) + 1u, drop.thr16, drop.scale, m2_, m3);
+        o.x *= m0; o.y *= m1_; o.z *= m2_; o.w *= m3;
+      }
+      if (b2) b2[lane + 32 * k] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      ac[k].x += o.x; ac[k].y += o.y; ac[k].z += o.z; ac[k].w += o.w;
+    }
+  }
+  // fold the warps' column partials: one warp at a time into shared memory, then one atomic per column and CTA
+  for (int w = 0; w < nwarps; ++w) {
+    if (wid == w) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4* a0 = reinterpret_cast<float4*>(sacc + 4 * (lane + 32 * k));
+        float4* a1 = reinterpret_cast<float4*>(sacc + d + 4 * (lane + 32 * k));
+        float4* a2 = reinterpret_cast<float4*>(sacc + 2 * d + 4 * (lane + 32 * k));
+        float4 t = *a0; t.x += ag[k].x; t.y += ag[k].y; t.z += ag[k].z; t.w += ag[k].w; *a0 = t;
+        t = *a1; t.x += ab[k].x; t.y += ab[k].y; t.z += ab[k].z; t.w += ab[k].w; *a1 = t;
+        t = *a2; t.x += ac[k].x; t.y += ac[k].y; t.z += ac[k].z; t.w += ac[k].w; *a2 = t;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[d + i]);
+    if (dx_colsum) atomicAdd(dx_colsum + i, sacc[2 * d + i]);
+  }
+}
+
 }  // namespace neko
 
 extern "C" {
@@ -350,6 +448,33 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
   int rows_per_cta = (N + ctas - 1) / ctas;
   rows_per_cta = ((rows_per_cta + LNB_ROWS - 1) / LNB_ROWS) * LNB_ROWS;
   ctas = (N + rows_per_cta - 1) / rows_per_cta;
+  // warp-per-row variant (default): d = 128 * NV with NV <= 8
+  static const bool force_cols = getenv("NEKO_LN_BWD_COLUMNS") != nullptr;
+  if (!force_cols && d % 128 == 0 && d <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx_resid)) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dy_bf16) & 7) == 0 && (!dx_bf16 || (reinterpret_cast<uintptr_t>(dx_bf16) & 7) == 0)) {
+    const int nv = d / 128;
+    const size_t smem_r = (size_t)4 * d * sizeof(float);
+    int grid = sm_count();
+    const int rows_per_grid = grid * 8;
+    if (N < rows_per_grid) grid = (N + 7) / 8;
+    const DropCfg dc = drop_cfg(branch_drop);
+#define NEKO_LNB_ROWS(NV_) launch_pdl(layernorm_bwd_rows_kernel<NV_>, dim3(grid), dim3(256), smem_r, as_stream(stream), \
+                                      reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid, reinterpret_cast<bf16*>(dx_bf16), \
+                                      dgamma, dbeta, dx_colsum, N, d, dc)
+    switch (nv) {
+      case 1: NEKO_LNB_ROWS(1); break;
+      case 2: NEKO_LNB_ROWS(2); break;
+      case 3: NEKO_LNB_ROWS(3); break;
+      case 4: NEKO_LNB_ROWS(4); break;
+      case 5: NEKO_LNB_ROWS(5); break;
+      case 6: NEKO_LNB_ROWS(6); break;
+      case 7: NEKO_LNB_ROWS(7); break;
+      default: NEKO_LNB_ROWS(8); break;
+    }
+#undef NEKO_LNB_ROWS
+    NEKO_LAUNCH_CHECK("layernorm_bwd_rows_kernel");
+    return NEKO_OK;
+  }
   // staged variant: ring of `stages` row blocks (40 d bytes each) in shared memory, two CTAs per SM
   const size_t stage_bytes = (size_t)LNB_ROWS * d * 10;
   int stages = (int)((100 * 1024) / stage_bytes);
