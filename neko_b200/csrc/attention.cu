@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       }
       // mask + online softmax (rows row_a, row_b; this thread holds keys j0 + n*8 + 2q, +1)
       float mx_a = -INFINITY, mx_b = -INFINITY;
-      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0) || (q0 + ATT_BLK > S_valid);
+      // rows beyond S_valid (right padding) are not masked here: they run on finite garbage and are zeroed at write-out
+      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0);
       if (need_mask) {
 #pragma unroll
         for (int n = 0; n < ATT_BLK / 8; ++n) {
@@ -228,6 +229,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
     l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
   }
   // write-out: dead rows (padding) -> zeros, lse = +inf so that backward sees p = 0
+  if (row_a < lo || row_a >= S_valid) l_a = 0.f;   // padding rows
+  if (row_b < lo || row_b >= S_valid) l_b = 0.f;
   const float inv_a = (l_a > 0.f) ? 1.f / l_a : 0.f, inv_b = (l_b > 0.f) ? 1.f / l_b : 0.f;
   const float kLn2 = 0.6931471805599453f;
   bf16* ob = out + (long long)b * S * d + h * DH;
@@ -369,7 +372,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
         }
       }
       // interior tiles (all keys valid and strictly below every query of the tile) need no per-element predicate
-      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0) || (q0 + ATT_BLK > S_valid);
+      // (rows beyond S_valid carry lse = +inf from the forward: their p is 0 without a predicate)
+      const bool need_mask = (j0 < lo) || (j0 + ATT_BLK > q0);
 #pragma unroll
       for (int n = 0; n < ATT_BLK / 8; ++n) {
         float p0 = ex2_ftz(fmaf(s[n][0], scale_log2, -lse_a)), p1 = ex2_ftz(fmaf(s[n][1], scale_log2, -lse_a));
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         }
       }
       // P^T = exp(S^T * scale - lse[query]); dS^T = P^T * (dP^T - delta[query]) * scale
-      const bool need_mask = (j0 < lo) || (i0 < j0 + ATT_BLK) || (i0 + ATT_BLK > S_valid);
+      const bool need_mask = (j0 < lo) || (i0 < j0 + ATT_BLK);   // queries beyond S_valid have lse = +inf -> p = 0
       const float* lsp = s_lse + buf * ATT_BLK;
       const float* dlp = s_delta + buf * ATT_BLK;
 #pragma unroll
