@@ -260,9 +260,12 @@ int neko_patch_pos_bwd(const float* dx, int P, int d, const int32_t* row_bin, co
  * fp32 parameter / gradient arena.
  * ------------------------------------------------------------------------------------------- */
 int neko_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream);
+/* w_f16 / w_bf16 (nullable): 16-bit operand copies of the first n_cast parameters (the GEMM weights), rewritten in the
+ * same pass so that the next forward needs no cast kernel. */
 int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                    const float* grad_sumsq, float max_norm, float grad_div, void* stream);
+                    const float* grad_sumsq, float max_norm, float grad_div,
+                    uint16_t* w_f16, uint16_t* w_bf16, int64_t n_cast, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ sumsq,
-                                                    float max_norm, float grad_div) {
+                                                    float max_norm, float grad_div, uint16_t* __restrict__ w_f16,
+                                                    uint16_t* __restrict__ w_bf16, long long n_cast) {
   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
   float coef = 1.0f / grad_div;
   if (sumsq != nullptr && max_norm > 0.f) {
@@ -46,7 +47,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+    pi = pi - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (i < n_cast) {   // refresh the 16-bit operand copies of the GEMM weights in the same pass
+      if (w_f16) w_f16[i] = cvt_16(pi, true);
+      if (w_bf16) w_bf16[i] = cvt_16(pi, false);
+    }
   }
 }
 
@@ -70,7 +76,7 @@ int neko_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream) {
 
 int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, const float* grad_sumsq, float max_norm,
-                    float grad_div, void* stream) {
+                    float grad_div, uint16_t* w_f16, uint16_t* w_bf16, int64_t n_cast, void* stream) {
   using namespace neko;
   NEKO_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1 && grad_div > 0.f, "adamw: bad arguments");
   if (n == 0) return NEKO_OK;
@@ -80,7 +86,8 @@ int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                               bc1, bc2_sqrt, grad_sumsq, max_norm, grad_div);
+                                                               bc1, bc2_sqrt, grad_sumsq, max_norm, grad_div, w_f16, w_bf16,
+                                                               (w_f16 || w_bf16) ? (long long)n_cast : 0LL);
   NEKO_LAUNCH_CHECK("adamw_kernel");
   return NEKO_OK;
 }

@@ -255,7 +255,8 @@ def sumsq(x: torch.Tensor, out: torch.Tensor):
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq=None, max_norm=0.0,
-               grad_div=1.0):
+               grad_div=1.0, w_f16=None, w_bf16=None, n_cast=0):
     check(load().neko_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), C.c_int64(param.numel()), C.c_float(lr),
                                  C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int(step),
-                                 _p(grad_sumsq), C.c_float(max_norm), C.c_float(grad_div), stream_ptr()), "neko_adamw_step")
+                                 _p(grad_sumsq), C.c_float(max_norm), C.c_float(grad_div), _p(w_f16), _p(w_bf16), C.c_int64(n_cast),
+                                 stream_ptr()), "neko_adamw_step")

@@ -742,7 +742,8 @@ class GatoPolicy(nn.Module):
         plan = st.plan
         d = self.embed_dim
         N = plan.B * plan.width
-        self._refresh_bf16(force=getattr(st, "in_graph", False))
+        if not getattr(st, "in_graph", False):   # graph mode: _engine_forward refreshed the copies eagerly, version-checked
+            self._refresh_bf16()
         if not getattr(st, "uploaded", False):
             self._image_upload(st)
         self._image_compute(st)
@@ -941,6 +942,9 @@ class GatoPolicy(nn.Module):
     def _engine_forward(self, st: _State):
         if not self.use_cuda_graphs:
             return self._forward_compute(st)
+        # 16-bit weight copies: refreshed OUTSIDE the graph, and only when a parameter changed since the last cast (an
+        # optimiser step, load_state_dict, ...); the captured kernels read the pointer-stable copies
+        self._refresh_bf16()
         self._image_upload(st)
         st.uploaded = True
         key = self._graph_key(st)
@@ -979,13 +983,14 @@ class GatoPolicy(nn.Module):
         cst.generation = self._generation
         ent["fwd"].replay()
         self.launches += ent["fwd_launches"]
-        self._bf16_versions = None
         st.__dict__.update(cst.__dict__)
         st.graph_entry = ent
         return ent["out"]
 
     def _stager_epoch(self):
-        return self._stager._dev.data_ptr() if self._stager._dev is not None else 0
+        """Addresses captured graphs depend on besides the workspace: the staging buffer and the 16-bit weight copies."""
+        return (self._stager._dev.data_ptr() if self._stager._dev is not None else 0, self._w16_arena.data_ptr(),
+                self._wbf_arena.data_ptr(), self._param_arena.data_ptr(), self._grad_arena.data_ptr())
 
     def _forward_compute(self, st: _State):
         plan = st.plan

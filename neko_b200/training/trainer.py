@@ -68,11 +68,18 @@ class FusedAdamW:
             self.sumsq.zero_()
             ops.sumsq(p._grad_arena, self.sumsq)
             ss = self.sumsq
+        # the update also rewrites the 16-bit operand copies of the GEMM weights (fp16 forward / bf16 backward), so the
+        # next forward starts without a cast kernel
+        dual = p.fwd_dtype == torch.float16 and p._w16_arena.dtype == torch.float16
+        w16 = p._w16_arena if dual else None
+        wbf = p._wbf_arena if dual else (p._w16_arena if p._w16_arena.dtype == torch.bfloat16 and p.fwd_dtype == torch.bfloat16 else None)
+        fused = (w16 is not None) or (wbf is not None)
         ops.adamw_step(p._param_arena, p._grad_arena, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                       self.eps, self.weight_decay, self.t, ss, max_norm, grad_div)
-        for q in p._params.values():   # the arena was updated in place: invalidate the 16-bit weight copies
-            q._version  # noqa: B018 (read-only attribute; the bump below is the supported way)
-        p._bf16_versions = None
+                       self.eps, self.weight_decay, self.t, ss, max_norm, grad_div, w_f16=w16, w_bf16=wbf,
+                       n_cast=p._cast_end if fused else 0)
+        # the arena was updated in place by raw pointers (no torch version bump): either the copies are fresh (fused) and
+        # the recorded versions stay valid, or they must be re-cast by the next forward
+        p._bf16_versions = tuple(q._version for q in p._params.values()) if fused else None
 
     def zero_grad(self):
         self.policy.zero_grad()

@@ -310,6 +310,9 @@ def test_adamw_clip(ops):
     g = _rand((n,), 52, 3.0)
     m = torch.zeros(n, device="cuda")
     v = torch.zeros(n, device="cuda")
+    n_cast = 60_001
+    w16 = torch.zeros(n_cast, device="cuda", dtype=torch.float16)
+    wbf = torch.zeros(n_cast, device="cuda", dtype=torch.bfloat16)
     pr = p.clone().requires_grad_(True)
     opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
     for step in range(1, 4):
@@ -318,8 +321,10 @@ def test_adamw_clip(ops):
         opt.step()
         ss = torch.zeros((), device="cuda")
         ops.sumsq(g, ss)
-        ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, ss, 1.0)
+        ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, ss, 1.0, w_f16=w16, w_bf16=wbf, n_cast=n_cast)
     assert (p - pr.detach()).abs().max().item() < 1e-5
+    # fused refresh of the 16-bit operand copies of the first n_cast parameters
+    assert torch.equal(w16, p[:n_cast].to(torch.float16)) and torch.equal(wbf, p[:n_cast].to(torch.bfloat16))
 
 
 # ---------------------------------------------------------------------------------------------------
