@@ -109,12 +109,16 @@ def run_reference(args):
     if rank != 0:
         return
     sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
-    tps, tokens, sec = cpu_oracle_tokens_per_s(args.config, sample, max(1, min(args.steps, 3)), 1)
+    # every step is a bounded sample of the workload (a few samples of the batch, ~0.3-1 s of CPU work); K and W are
+    # honoured up to a cap that keeps the whole run within a couple of minutes
+    steps, warm = max(1, min(args.steps, 60)), max(1, min(args.warmup, 5))
+    tps, tokens, sec = cpu_oracle_tokens_per_s(args.config, sample, steps, warm)
     cores = os.cpu_count() or 1
-    desc = f"fwd+bwd over {sample} samples of the {args.config} batch ({tokens} tokens) per step, fp32 torch-CPU, {cores} threads"
+    desc = (f"fwd+bwd over {sample} samples of the {args.config} batch ({tokens} tokens) per step, fp32 torch-CPU, {cores} threads, "
+            f"{steps} timed steps after {warm} warm-up")
     print(json.dumps({
         "impl": "reference", "metric": "train tokens/sec (fwd+bwd)", "value": round(tps, 2), "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOADS[args.config], "name": args.config},
         "cpu_baseline": {"value": round(tps, 2), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(tps, 2), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -73,6 +73,7 @@ class TrainingArgs:
     save_dir: str = "models"
     # synthetic-data additions of this repo (no datasets / simulators offline)
     synthetic: str = "cfg2"
+    disable_cuda_graphs: bool = False   # replay forward / backward from CUDA graphs per batch shape (neko_b200 engine knob)
     seed: int = 1234
 
 

@@ -39,6 +39,7 @@ def main():
     if args.dropout == 0:
         model.transformer.drop.p = 0.0
     model.materialize_logits = False   # the trainer discards logits (trainer.py:178)
+    model.use_cuda_graphs = not args.disable_cuda_graphs
     sync = None
     if world > 1:
         dp.broadcast_parameters(model)
