@@ -202,6 +202,15 @@ int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int3
                        void* stream);
 /* dlogits bf16 rows get (softmax - onehot) * (*gscale) / n_rows; in the dense layout the caller
  * zero-fills the buffer beforehand.  gscale: device fp32 scalar (upstream d loss). */
+/* Training forward: loss AND the gradient operand in one pass over the selected rows (each row is read from HBM once and
+ * kept in shared memory): dlogits = (softmax - onehot) / n_rows as bf16, i.e. neko_masked_ce_bwd with gscale = 1.
+ * Returns 1 (nothing launched) when a row does not fit the shared memory of one CTA or the buffers are not vector-aligned:
+ * the caller then uses neko_masked_ce_fwd / neko_masked_ce_bwd.  neko_ce_scale_grad multiplies the stored gradient by the
+ * upstream scalar in backward and is a no-op on the device when that scalar is exactly 1. */
+int neko_masked_ce_fused(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
+                         const int64_t* tokens, float* row_lse, float* row_loss, float* loss,
+                         uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream);
+int neko_ce_scale_grad(uint16_t* dlogits, int64_t n, const float* gscale, void* stream);
 int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
                        const int64_t* tokens, const float* row_lse, const float* gscale,
                        uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream);

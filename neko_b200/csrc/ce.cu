@@ -116,6 +116,99 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
     for (long long i = V + threadIdx.x; i < ldd; i += CE_THREADS) dz[i] = __float2bfloat16_rn(0.f);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused forward + gradient (training): one CTA keeps a whole logits row (V fp32 = 209 KB at V = 52 305) in shared
+// memory, so the row is read from HBM ONCE: max -> exp / sum -> loss, then (softmax - onehot) / n_rows is written as the
+// bf16 dlogits operand of the head backward GEMMs.  The separate kernels above read every selected row twice (forward,
+// backward).  The upstream gradient of the loss is not known yet in forward: backward multiplies by it only when it is
+// not exactly 1 (ce_scale_kernel: gradient accumulation divides the loss, plain loss.backward() does not).
+// ---------------------------------------------------------------------------------------------
+constexpr int CEF_THREADS = 1024;
+
+__device__ __forceinline__ float cef_block_reduce(float v, bool is_max, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();   // protects `red` against the previous use
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < CEF_THREADS / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                                  const int32_t* __restrict__ rows, int n_rows,
+                                                                  const int64_t* __restrict__ tokens, float* __restrict__ row_lse,
+                                                                  float* __restrict__ row_loss, bf16* __restrict__ dlogits, long long ldd,
+                                                                  int flags) {
+  extern __shared__ __align__(16) float cef_row[];   // [V rounded up to 4]
+  __shared__ float red[CEF_THREADS / 32];
+  const int nv = V >> 2;
+  const float inv_n = 1.0f / (float)n_rows;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const long long pos = rows[r];
+    const float* z = logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : pos) * ld;
+    bf16* dz = dlogits + ((flags & NEKO_CE_DLOGITS_COMPACT) ? (long long)r : pos) * ldd;
+    // pass 1: HBM -> shared memory, running maximum
+    float mx = -INFINITY;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    float4* s4 = reinterpret_cast<float4*>(cef_row);
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      const float4 v = __ldg(z4 + i);
+      s4[i] = v;
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) { const float v = z[i]; cef_row[i] = v; mx = fmaxf(mx, v); }
+    mx = cef_block_reduce(mx, true, red);
+    // pass 2 (shared memory): e = exp(z - max), sum
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      float4 v = s4[i];
+      v.x = __expf(v.x - mx); v.y = __expf(v.y - mx); v.z = __expf(v.z - mx); v.w = __expf(v.w - mx);
+      s4[i] = v;
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) { const float e = __expf(cef_row[i] - mx); cef_row[i] = e; sum += e; }
+    sum = cef_block_reduce(sum, false, red);
+    const int tgt = (int)tokens[pos + 1];
+    if (threadIdx.x == 0) {
+      const float lse = mx + logf(sum);
+      row_lse[r] = lse;
+      row_loss[r] = (tgt >= 0 && tgt < V) ? lse - z[tgt] : 0.f;
+    }
+    // pass 3 (shared memory -> HBM): (softmax - onehot) / n_rows as bf16
+    const float sc = inv_n / sum;
+    uint2* d2 = reinterpret_cast<uint2*>(dz);
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      const float4 v = s4[i];
+      const int c = i << 2;
+      d2[i] = make_uint2(pack_bf16x2(v.x * sc - (c == tgt ? inv_n : 0.f), v.y * sc - (c + 1 == tgt ? inv_n : 0.f)),
+                         pack_bf16x2(v.z * sc - (c + 2 == tgt ? inv_n : 0.f), v.w * sc - (c + 3 == tgt ? inv_n : 0.f)));
+    }
+    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) dz[i] = __float2bfloat16_rn(cef_row[i] * sc - (i == tgt ? inv_n : 0.f));
+    if (flags & NEKO_CE_ZERO_PAD)
+      for (long long i = V + threadIdx.x; i < ldd; i += CEF_THREADS) dz[i] = __float2bfloat16_rn(0.f);
+    __syncthreads();   // the row buffer is reused by the next row
+  }
+}
+
+// dlogits *= g unless g == 1 (bf16 [n_rows, ld], all columns)
+__global__ void __launch_bounds__(256) ce_scale_kernel(bf16* __restrict__ d, long long n8, const float* __restrict__ gscale) {
+  const float g = __ldg(gscale);
+  if (g == 1.0f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v = reinterpret_cast<uint4*>(d)[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(w[j]); w[j] = pack_bf16x2(f.x * g, f.y * g); }
+    reinterpret_cast<uint4*>(d)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 }  // namespace neko
 
 extern "C" {
@@ -141,6 +234,42 @@ int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int3
   ce_bwd_kernel<<<n_rows, CE_THREADS, 0, as_stream(stream)>>>(logits, ld_logits, V, rows, n_rows, tokens, row_lse, gscale,
                                                              reinterpret_cast<bf16*>(dlogits), ldd, flags);
   NEKO_LAUNCH_CHECK("ce_bwd_kernel");
+  return NEKO_OK;
+}
+
+int neko_masked_ce_fused(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
+                         float* row_lse, float* row_loss, float* loss, uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(logits && rows && tokens && row_lse && row_loss && loss && dlogits, "masked_ce_fused: null pointer");
+  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V && ld_dlogits >= V, "masked_ce_fused: bad sizes");
+  const size_t smem = ((size_t)V + 3) / 4 * 16;
+  // the row must fit the CTA's shared memory, and the vector paths need aligned pitches: otherwise report "not applicable"
+  if (smem > 220 * 1024 || (ld_logits & 3) || (ld_dlogits & 3) || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(dlogits) & 7))
+    return 1;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(ce_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ce_fused)");
+    attr = smem;
+  }
+  const int grid = n_rows < sm_count() ? n_rows : sm_count();
+  ce_fused_kernel<<<grid, CEF_THREADS, smem, as_stream(stream)>>>(logits, ld_logits, V, rows, n_rows, tokens, row_lse, row_loss,
+                                                                  reinterpret_cast<bf16*>(dlogits), ld_dlogits, flags);
+  NEKO_LAUNCH_CHECK("ce_fused_kernel");
+  ce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_rows, loss);
+  NEKO_LAUNCH_CHECK("ce_mean_kernel");
+  return NEKO_OK;
+}
+
+int neko_ce_scale_grad(uint16_t* dlogits, int64_t n, const float* gscale, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(dlogits && gscale && n > 0 && n % 8 == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0, "ce_scale_grad: bad arguments");
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  ce_scale_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<bf16*>(dlogits), n8, gscale);
+  NEKO_LAUNCH_CHECK("ce_scale_kernel");
   return NEKO_OK;
 }
 

@@ -194,6 +194,24 @@ def masked_ce_fwd(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torc
     return loss, row_lse, row_loss
 
 
+def masked_ce_fused(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: torch.Tensor, dlogits: torch.Tensor, flags: int = 0):
+    """Loss + unscaled gradient operand in one pass (training).  Returns (loss, row_lse) or None when not applicable."""
+    n = rows.numel()
+    row_lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+    row_loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    rc = load().neko_masked_ce_fused(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens), _p(row_lse),
+                                     _p(row_loss), _p(loss), _p(dlogits), C.c_int64(dlogits.stride(-2)), C.c_int(flags), stream_ptr())
+    if rc == 1:
+        return None
+    check(rc, "neko_masked_ce_fused")
+    return loss, row_lse
+
+
+def ce_scale_grad(dlogits: torch.Tensor, gscale: torch.Tensor):
+    check(load().neko_ce_scale_grad(_p(dlogits), C.c_int64(dlogits.numel()), _p(gscale), stream_ptr()), "neko_ce_scale_grad")
+
+
 def masked_ce_bwd(logits, V, rows, tokens, row_lse, gscale, dlogits, flags: int = 0):
     n = rows.numel()
     ld = dlogits.stride(-2)

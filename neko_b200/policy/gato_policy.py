@@ -1012,8 +1012,7 @@ class GatoPolicy(nn.Module):
                 if n_rows == 0:
                     loss = torch.full((), float("nan"), device=self.device)  # mean over an empty selection
                 else:
-                    loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens)
-                    self.launches += 2
+                    loss = self._ce_forward(st, full, V, n_rows, keep, 0)
         else:
             logits = torch.empty(0, device=self.device)
             if st.compute_loss and n_rows:
@@ -1021,9 +1020,25 @@ class GatoPolicy(nn.Module):
                 ops.gather_rows(hf, st.loss_rows, d, hc)
                 full = self._head(hc, n_rows)
                 st.logits_full, st.hf_rows = full, hc
-                loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens, flags=ops.CE_LOGITS_COMPACT)
-                self.launches += 3
+                loss = self._ce_forward(st, full, V, n_rows, keep, ops.CE_LOGITS_COMPACT)
+                self.launches += 1
         return logits, loss
+
+    def _ce_forward(self, st: _State, full: torch.Tensor, V: int, n_rows: int, keep: bool, flags: int):
+        """Masked cross entropy (gato_policy.py:174-186).  With gradients wanted and the compact head backward, the loss
+        and the (unscaled) dlogits operand come out of ONE pass over the selected rows (ce_fused_kernel)."""
+        st.ce_fused = False
+        if keep and (self.head_mode == "rows" or not self.materialize_logits):
+            dl = self._buf("dlogits_rows", (n_rows, self._Vp), torch.bfloat16)
+            out = ops.masked_ce_fused(full, V, st.loss_rows, st.tokens, dl, flags=flags | ops.CE_DLOGITS_COMPACT | ops.CE_ZERO_PAD)
+            if out is not None:
+                st.ce_fused = True
+                self.launches += 2
+                loss, st.row_lse = out
+                return loss
+        loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens, flags=flags)
+        self.launches += 2
+        return loss
 
     # ------------------------------------------------------------------------------------------
     # backward engine
@@ -1091,7 +1106,10 @@ class GatoPolicy(nn.Module):
             dl = self._buf("dlogits_rows", (n_rows, Vp), torch.bfloat16)
             # the kernel also zeroes the pad columns V..Vp (K tail of the dgrad GEMM)
             flags = ops.CE_DLOGITS_COMPACT | ops.CE_ZERO_PAD | (ops.CE_LOGITS_COMPACT if compact_logits else 0)
-            ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl, flags=flags)
+            if getattr(st, "ce_fused", False):   # forward already wrote (softmax - onehot) / n: apply the upstream scalar
+                ops.ce_scale_grad(dl, gscale)
+            else:
+                ops.masked_ce_bwd(st.logits_full, V, st.loss_rows, st.tokens, st.row_lse, gscale, dl, flags=flags)
             hc = self._buf("hf_rows_b", (n_rows, d), torch.bfloat16)
             ops.gather_rows(st.hf, st.loss_rows, d, hc)
             ops.gemm(dl, hc, a_mn=True, b_mn=True, epilogue=ops.EPI_F32, out=G("predict_token.weight"), accumulate=acc,

@@ -517,3 +517,36 @@ def test_attention_tensor_core_forward_long(ops, monkeypatch, tc, B, S, H, dh, S
     dout = _rand((B, S, d), 24, 1.0, torch.bfloat16) * live
     dqkv = ops.attention_bwd(qkv, out, dout, lse, fv, H, S_valid)
     assert torch.isfinite(dqkv.float()).all()
+
+
+@pytest.mark.parametrize("V,ld", [(2208, 2208), (52305, 52352), (1001, 1004)])
+def test_masked_ce_fused_matches_two_pass(ops, V, ld):
+    """ce_fused_kernel (loss + unscaled dlogits in one pass) against the separate forward / backward kernels, and the
+    conditional scale in backward."""
+    B, S = 3, 40
+    N = B * S
+    g = torch.Generator(device="cpu").manual_seed(V)
+    store = torch.zeros(N, ld, device="cuda")
+    store[:, :V] = (torch.randn(N, V, generator=g) * 3).cuda()
+    tokens = torch.randint(0, V, (N,), generator=g).cuda()
+    rows = torch.arange(0, N - 1, 3, dtype=torch.int32).cuda()
+    n = rows.numel()
+    ldd = (V + 63) // 64 * 64
+    loss_ref, lse_ref, _ = ops.masked_ce_fwd(store, V, rows, tokens)
+    one = torch.ones((), device="cuda")
+    d_ref = torch.full((n, ldd), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.masked_ce_bwd(store, V, rows, tokens, lse_ref, one, d_ref, flags=ops.CE_DLOGITS_COMPACT | ops.CE_ZERO_PAD)
+    d_new = torch.full((n, ldd), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = ops.masked_ce_fused(store, V, rows, tokens, d_new, flags=ops.CE_DLOGITS_COMPACT | ops.CE_ZERO_PAD)
+    assert out is not None
+    loss, lse = out
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    assert (lse - lse_ref).abs().max().item() <= 1e-4
+    assert (d_new.float() - d_ref.float()).abs().max().item() <= 2.0 ** -8 * d_ref.float().abs().max().item() + 1e-8
+    assert float(d_new[:, V:].abs().max()) == 0.0 if ldd > V else True
+    # upstream scalar: exactly 1 leaves the buffer untouched, anything else scales it
+    keep = d_new.clone()
+    ops.ce_scale_grad(d_new, one)
+    assert torch.equal(d_new, keep)
+    ops.ce_scale_grad(d_new, torch.full((), 0.25, device="cuda"))
+    assert torch.equal(d_new, (keep.float() * 0.25).to(torch.bfloat16))
