@@ -249,7 +249,7 @@ def run_ours(args):
     import torch.distributed as dist
     from neko_b200 import dp, ops
     from neko_b200.policy import GatoPolicy
-    from oracle import gato_oracle as O  # synthetic-input generator + config table only (no oracle compute on this arm)
+    from neko_b200.tasks.synthetic import BENCH_CONFIGS, bench_batch   # the GPU arm never touches oracle/
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,7 +258,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfgd = O.CONFIGS[args.config]
+    cfgd = {k: v for k, v in BENCH_CONFIGS[args.config].items() if k != "batch"}
 
     class _Tok:
         vocab_size = 50257
@@ -275,10 +275,10 @@ def run_ours(args):
     if world > 1:
         dp.broadcast_parameters(model)
         # static knowledge of the task mix, as a trainer has it from --text_prop / --caption_prop / --vqa_prop
-        no_text = not any(("text" in s and s["text"] is not None) for s in O.synth_batch(args.config, seed=0))
+        no_text = not any(("text" in s and s["text"] is not None) for s in bench_batch(args.config, seed=0))
         bucket_mb = int(os.environ.get("NEKO_DP_BUCKET_MB", "64"))
         sync = dp.attach(model, bucket_bytes=bucket_mb << 20, no_text_tokens=no_text)
-    host_batch = O.synth_batch(args.config, seed=1234 + rank)
+    host_batch = bench_batch(args.config, seed=1234 + rank)
     dev_batch = to_device(host_batch, dev)
     pin_batch = to_pinned(host_batch)
     tokens_per_step = int(sum(1 for _ in range(0)) or 0)

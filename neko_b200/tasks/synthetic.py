@@ -98,3 +98,41 @@ def build_synthetic_tasks(name: str, seed: int = 1234, device=None, pin: bool = 
         return [SyntheticTextTask(seed=seed, **kw), SyntheticCaptionTask(seed=seed + 1, **kw), SyntheticVqaTask(seed=seed + 2, **kw),
                 SyntheticControlTask(17, 6, seed=seed + 3, **kw), SyntheticControlTask(image_hw=96, seed=seed + 4, **kw)]
     raise ValueError(name)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The five BASELINE.json configurations as (model hyper-parameters, one batch of the config's shape); bench.py's GPU arm
+# draws its inputs from here (SURVEY.md section 8(d) "synthetic inputs").
+# ---------------------------------------------------------------------------------------------------------
+BENCH_CONFIGS = {
+    "cfg1": dict(embed_dim=128, layers=3, heads=1, context_len=240, batch=4),
+    "cfg2": dict(embed_dim=768, layers=6, heads=24, context_len=240, batch=32),
+    "cfg3": dict(embed_dim=768, layers=6, heads=24, context_len=512, batch=32),
+    "cfg4": dict(embed_dim=768, layers=6, heads=24, context_len=1024, batch=16),
+    "cfg5": dict(embed_dim=768, layers=6, heads=24, context_len=1024, batch=32),
+}
+
+
+def bench_batch(name: str, seed: int = 1234) -> List[dict]:
+    """One host-resident batch of configuration `name` (list of dicts, reference input contract)."""
+    c = BENCH_CONFIGS[name]
+    B, k = c["batch"], c["context_len"]
+    if name == "cfg1":
+        return SyntheticControlTask(17, 6, seed=seed).sample_batch(B, max_tokens=k)
+    if name == "cfg2":   # halfcheetah / hopper / walker2d shapes, cycling
+        tasks = [SyntheticControlTask(17, 6, seed=seed), SyntheticControlTask(11, 3, seed=seed + 1), SyntheticControlTask(17, 6, seed=seed + 2)]
+        return [tasks[i % 3].sample_batch(1, max_tokens=k)[0] for i in range(B)]
+    if name == "cfg3":   # Breakout-shaped frames: 84x84 gray -> 3 channels, zero-padded to 96x96 (control_task.py:380-389)
+        return SyntheticControlTask(image_hw=96, seed=seed).sample_batch(B, max_tokens=k)
+    if name == "cfg4":
+        return SyntheticTextTask(seed=seed).sample_batch(B, max_tokens=k)
+    if name == "cfg5":   # text .25 / caption .25 / vqa .25 / control .25 (half MuJoCo-shaped, half Atari-shaped)
+        q = B // 4
+        rest = B - 3 * q
+        out = SyntheticTextTask(seed=seed).sample_batch(q, max_tokens=k)
+        out += SyntheticCaptionTask(seed=seed + 1).sample_batch(q)
+        out += SyntheticVqaTask(seed=seed + 2).sample_batch(q)
+        out += SyntheticControlTask(17, 6, seed=seed + 3).sample_batch(rest // 2, max_tokens=k)
+        out += SyntheticControlTask(image_hw=96, seed=seed + 4).sample_batch(rest - rest // 2, max_tokens=k)
+        return out
+    raise ValueError(name)
