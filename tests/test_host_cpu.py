@@ -170,3 +170,36 @@ def test_grad_synchronizer_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
+
+
+def test_bench_batches_have_the_oracle_configs_shapes():
+    """bench.py's GPU arm draws inputs from the package; they must have the shapes / dtypes of the oracle's generator
+    (the one the golden fixtures and the CPU baseline use) for every BASELINE configuration."""
+    from neko_b200.tasks.synthetic import BENCH_CONFIGS, bench_batch
+    for n in BENCH_CONFIGS:
+        a, b = O.synth_batch(n, seed=1), bench_batch(n, seed=1)
+        assert len(a) == len(b) == BENCH_CONFIGS[n]["batch"], n
+        for x, y in zip(a, b):
+            assert set(x) == set(y), (n, set(x), set(y))
+            for k in x:
+                sx = tuple(x[k].shape) if hasattr(x[k], "shape") else (len(x[k]),)
+                sy = tuple(y[k].shape) if hasattr(y[k], "shape") else (len(y[k]),)
+                assert sx == sy, (n, k, sx, sy)
+                if hasattr(x[k], "dtype"):
+                    assert x[k].dtype == y[k].dtype, (n, k)
+        assert {k: v for k, v in BENCH_CONFIGS[n].items() if k != "batch"} == O.CONFIGS[n]
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: neither the package nor the GPU arm of bench.py may import it."""
+    import re
+    for dirpath, _dirs, files in os.walk(os.path.join(ROOT, "neko_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+    src = open(os.path.join(ROOT, "train.py")).read()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = bench[bench.index("def run_ours("):bench.index("def main(")]
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", gpu_arm, flags=re.M)   # (its cpu_baseline leg calls cpu_oracle_tokens_per_s)
