@@ -269,7 +269,7 @@ int neko_colsum_bf16(const uint16_t* X, int64_t ld, int M, int N, float* out, in
   }
   if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
     const int cb = (N + 255) / 256;
-    int chunks = (sm_count() * 4 + cb - 1) / cb;
+    int chunks = (sm_count() * 8 + cb - 1) / cb;     // ~8 resident CTAs per SM (32 registers, 8 KB shared memory each)
     if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
     if (chunks < 1) chunks = 1;
     const int rpc = (M + chunks - 1) / chunks;
