@@ -326,23 +326,23 @@ __global__ void __launch_bounds__(512) layernorm_bwd_staged_kernel(const bf16* _
 // memory (warp after warp, no atomics) before ONE global atomicAdd per column.  ~200 warp-instructions per row.
 // ---------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256, 1) layernorm_bwd_rows_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_rows_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd, float* __restrict__ dx_resid,
                                                                     bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                                                                     float* __restrict__ dbeta, float* __restrict__ dx_colsum, int N, int d,
                                                                     DropCfg drop) {
-  extern __shared__ __align__(16) float lnr_s[];      // gamma [d] | acc [3][d]
+  // shared memory: gamma [d] | per-warp column accumulators [nwarps][3][d] (dgamma, dbeta, colsum).  Keeping the
+  // accumulators out of the register file (72 registers at d = 768) lets two CTAs share an SM: twice the rows in flight.
+  extern __shared__ __align__(16) float lnr_s[];
   float* sg = lnr_s;
-  float* sacc = lnr_s + d;
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { sg[i] = gamma[i]; sacc[i] = 0.f; sacc[d + i] = 0.f; sacc[2 * d + i] = 0.f; }
+  float* wacc = lnr_s + d + (size_t)wid * 3 * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) sg[i] = gamma[i];
+  for (int i = lane; i < 3 * d; i += 32) wacc[i] = 0.f;
   __syncthreads();
-  float4 ag[NV], ab[NV], ac[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) ag[k] = ab[k] = ac[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_d = 1.0f / (float)d;
   const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
   const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
@@ -359,15 +359,21 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_rows_kernel(const bf16* 
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * (lane + 32 * k));
+      const int c4 = lane + 32 * k;
+      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c4);
       const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
-      // xv <- xhat ; keep dy * gamma in place of rv's partner via recomputation below
-      xv[k] = make_float4((xv[k].x - mu) * rs, (xv[k].y - mu) * rs, (xv[k].z - mu) * rs, (xv[k].w - mu) * rs);
+      xv[k] = make_float4((xv[k].x - mu) * rs, (xv[k].y - mu) * rs, (xv[k].z - mu) * rs, (xv[k].w - mu) * rs);   // xhat
       const float g0 = d01.x * g.x, g1 = d01.y * g.y, g2 = d23.x * g.z, g3 = d23.y * g.w;
       s1 += (g0 + g1) + (g2 + g3);
       s2 += (g0 * xv[k].x + g1 * xv[k].y) + (g2 * xv[k].z + g3 * xv[k].w);
-      ab[k].x += d01.x; ab[k].y += d01.y; ab[k].z += d23.x; ab[k].w += d23.y;
-      ag[k].x += d01.x * xv[k].x; ag[k].y += d01.y * xv[k].y; ag[k].z += d23.x * xv[k].z; ag[k].w += d23.y * xv[k].w;
+      float4* ag = reinterpret_cast<float4*>(wacc + 4 * c4);
+      float4* ab = reinterpret_cast<float4*>(wacc + d + 4 * c4);
+      float4 t = *ag;
+      t.x += d01.x * xv[k].x; t.y += d01.y * xv[k].y; t.z += d23.x * xv[k].z; t.w += d23.y * xv[k].w;
+      *ag = t;
+      t = *ab;
+      t.x += d01.x; t.y += d01.y; t.z += d23.x; t.w += d23.y;
+      *ab = t;
     }
     const float m1 = warp_sum(s1) * inv_d, m2 = warp_sum(s2) * inv_d;
     uint32_t rk = 0u;
@@ -375,43 +381,41 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_rows_kernel(const bf16* 
     uint2* b2 = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + off) : nullptr;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * (lane + 32 * k));
+      const int c4 = lane + 32 * k;
+      const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c4);
       const float2 d01 = unpack_bf16x2(dv[k].x), d23 = unpack_bf16x2(dv[k].y);
       float4 o = rv[k];
       o.x += rs * (d01.x * g.x - m1 - xv[k].x * m2);
       o.y += rs * (d01.y * g.y - m1 - xv[k].y * m2);
       o.z += rs * (d23.x * g.z - m1 - xv[k].z * m2);
       o.w += rs * (d23.y * g.w - m1 - xv[k].w * m2);
-      r4[lane + 32 * k] = o;
+      r4[c4] = o;
       if (drop.seed) {  // gradient entering the dropped-out residual branch: mask * scale * dx
         float m0, m1_, m2_, m3;
-        drop_pair(rk, 2u * (lane + 32 * k), drop.thr16, drop.scale, m0, m1_);
-        drop_pair(rk, 2u * (lane + 32 * k) + 1u, drop.thr16, drop.scale, m2_, m3);
+        drop_pair(rk, 2u * c4, drop.thr16, drop.scale, m0, m1_);
+        drop_pair(rk, 2u * c4 + 1u, drop.thr16, drop.scale, m2_, m3);
         o.x *= m0; o.y *= m1_; o.z *= m2_; o.w *= m3;
       }
-      if (b2) b2[lane + 32 * k] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      ac[k].x += o.x; ac[k].y += o.y; ac[k].z += o.z; ac[k].w += o.w;
-    }
-  }
-  // fold the warps' column partials: one warp at a time into shared memory, then one atomic per column and CTA
-  for (int w = 0; w < nwarps; ++w) {
-    if (wid == w) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float4* a0 = reinterpret_cast<float4*>(sacc + 4 * (lane + 32 * k));
-        float4* a1 = reinterpret_cast<float4*>(sacc + d + 4 * (lane + 32 * k));
-        float4* a2 = reinterpret_cast<float4*>(sacc + 2 * d + 4 * (lane + 32 * k));
-        float4 t = *a0; t.x += ag[k].x; t.y += ag[k].y; t.z += ag[k].z; t.w += ag[k].w; *a0 = t;
-        t = *a1; t.x += ab[k].x; t.y += ab[k].y; t.z += ab[k].z; t.w += ab[k].w; *a1 = t;
-        t = *a2; t.x += ac[k].x; t.y += ac[k].y; t.z += ac[k].z; t.w += ac[k].w; *a2 = t;
+      if (b2) b2[c4] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      if (dx_colsum) {
+        float4* ac = reinterpret_cast<float4*>(wacc + 2 * d + 4 * c4);
+        float4 t = *ac;
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        *ac = t;
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
+  // fold the warps' slices: one thread per column, one global atomic per column and CTA
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(dgamma + i, sacc[i]);
-    atomicAdd(dbeta + i, sacc[d + i]);
-    if (dx_colsum) atomicAdd(dx_colsum + i, sacc[2 * d + i]);
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      const float* s = lnr_s + d + (size_t)w * 3 * d;
+      a += s[i]; b += s[d + i]; c += s[2 * d + i];
+    }
+    atomicAdd(dgamma + i, a);
+    atomicAdd(dbeta + i, b);
+    if (dx_colsum) atomicAdd(dx_colsum + i, c);
   }
 }
 
@@ -453,12 +457,17 @@ int neko_layernorm_bwd(const uint16_t* dy_bf16, const float* x, const float* gam
   if (!force_cols && d % 128 == 0 && d <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx_resid)) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy_bf16) & 7) == 0 && (!dx_bf16 || (reinterpret_cast<uintptr_t>(dx_bf16) & 7) == 0)) {
     const int nv = d / 128;
-    const size_t smem_r = (size_t)4 * d * sizeof(float);
-    int grid = sm_count();
+    const size_t smem_r = (size_t)(1 + 8 * 3) * d * sizeof(float);   // gamma + 8 warps x 3 accumulator rows
+    int grid = 2 * sm_count();                                       // two CTAs per SM
     const int rows_per_grid = grid * 8;
     if (N < rows_per_grid) grid = (N + 7) / 8;
     const DropCfg dc = drop_cfg(branch_drop);
-#define NEKO_LNB_ROWS(NV_) launch_pdl(layernorm_bwd_rows_kernel<NV_>, dim3(grid), dim3(256), smem_r, as_stream(stream), \
+#define NEKO_LNB_ROWS(NV_) { static bool attr_##NV_ = false;                                                                      \
+      if (!attr_##NV_) {                                                                                                          \
+        cudaError_t e_ = cudaFuncSetAttribute(layernorm_bwd_rows_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024); \
+        if (e_ != cudaSuccess) return check_cuda(e_, "cudaFuncSetAttribute(layernorm_bwd_rows)");                                    \
+        attr_##NV_ = true; } }                                                                                                      \
+    launch_pdl(layernorm_bwd_rows_kernel<NV_>, dim3(grid), dim3(256), smem_r, as_stream(stream), \
                                       reinterpret_cast<const bf16*>(dy_bf16), x, gamma, mean, rstd, dx_resid, reinterpret_cast<bf16*>(dx_bf16), \
                                       dgamma, dbeta, dx_colsum, N, d, dc)
     switch (nv) {
