@@ -693,7 +693,8 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   // outputs (LM head, weight gradients) and wide 16-bit outputs; narrow-N and epilogue-heavy launches stay single-CTA.
   // (tools/gemm_sweep.py: at K >= 2048 the 256 x 256 pair tile also wins for N = 768 despite filling only 1.2 waves.)
   const bool plain16 = (epilogue == NEKO_EPI_BF16), resid = (epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_RESID_F32_BF16);
-  int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (plain16 && (N >= 2048 || K >= 2048)) || (resid && K >= 2048)) ? 1 : 0;
+  const bool gelu_wide = (epilogue == NEKO_EPI_GELU_BF16 && N >= 2048);   // 57.4 vs 59.4 us at M=7680, 104 vs 113 us at M=15808
+  int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (plain16 && (N >= 2048 || K >= 2048)) || (resid && K >= 2048) || gelu_wide) ? 1 : 0;
   if (const char* force = getenv("NEKO_GEMM_PAIR")) { pair_lo = pair_hi = atoi(force) ? 1 : 0; }
   double best = 1e30;
   p.BN = 128; p.splits = 1; p.pair = 0;
