@@ -396,7 +396,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = 2u * BN;  // 256 or 512: a power of two >= 32
+  const uint32_t tmem_cols = (2u * BN <= 256u) ? 256u : 512u;  // two accumulator stages of BN columns, rounded to a power of two
   pdl_launch_dependents();             // the next kernel of the stream may start its own prologue as SMs free up
 
   if (warp == 0 && lane == 0) {
@@ -697,25 +697,35 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   int pair_lo = 0, pair_hi = (epilogue == NEKO_EPI_F32 || (plain16 && (N >= 2048 || K >= 2048)) || (resid && K >= 2048) || gelu_wide) ? 1 : 0;
   if (const char* force = getenv("NEKO_GEMM_PAIR")) { pair_lo = pair_hi = atoi(force) ? 1 : 0; }
   double best = 1e30;
+  // BN = 192 is implemented and tested (NEKO_GEMM_BN=192) but not chosen automatically: at the N = 768 shapes it measured
+  // within +-2 us of the 128 / 256 choices (the main loop is bound by operand traffic, not by wave count)
+  static const bool no192 = getenv("NEKO_GEMM_AUTO192") == nullptr;
   p.BN = 128; p.splits = 1; p.pair = 0;
   for (int pr = pair_lo; pr <= pair_hi; ++pr) {
     const long long mb_ = (M + (pr ? 2 * BM : BM) - 1) / (pr ? 2 * BM : BM);
     const int workers = pr ? sms / 2 : sms;
-    for (int bn = 128; bn <= 256; bn += 128) {
-      if (bn == 256 && N <= 128) break;
-      const double kb_cost = pr ? (bn == 128 ? 1.15 : 1.4) : (bn == 128 ? 1.15 : 1.6);   // fitted to tools/gemm_sweep.py
+    for (int bn = 128; bn <= 256; bn += 64) {
+      if (bn > 128 && N <= 128) break;
+      // BN = 192 (4 x 192 = 768: fewer, fuller waves at the N = 768 shapes); a CTA of a pair would stage 96 rows of B, which
+      // the 64-wide boxes of an MN-major operand cannot express
+      if (bn == 192 && ((pr && b_mn) || no192)) continue;
+      const double kb_cost = pr ? (bn == 128 ? 1.15 : (bn == 192 ? 1.27 : 1.4))
+                                : (bn == 128 ? 1.15 : (bn == 192 ? 1.38 : 1.6));   // fitted to tools/gemm_sweep.py
       const long long tiles_ = mb_ * ((N + bn - 1) / bn);
       for (int sp = 1; sp <= (can_split ? 16 : 1); ++sp) {
         if (sp > 1 && kblocks / sp < 8) break;
         const long long units_ = tiles_ * sp;
-        const double per_unit = ((kblocks + sp - 1) / sp) * kb_cost + 3.0 * (bn / 128) * (sp > 1 ? 1.5 : 1.0);
+        const double per_unit = ((kblocks + sp - 1) / sp) * kb_cost + 3.0 * (bn / 128.0) * (sp > 1 ? 1.5 : 1.0);
         const double cost = (double)((units_ + workers - 1) / workers) * per_unit;
         if (cost < best - 1e-9) { best = cost; p.BN = bn; p.splits = sp; p.pair = pr; }
       }
     }
   }
   const long long mb_ = (M + (p.pair ? 2 * BM : BM) - 1) / (p.pair ? 2 * BM : BM);
-  if (const char* force = getenv("NEKO_GEMM_BN")) { const int v = atoi(force); if (v == 128 || v == 256) p.BN = v; }
+  if (const char* force = getenv("NEKO_GEMM_BN")) {
+    const int v = atoi(force);
+    if (v == 128 || v == 256 || (v == 192 && !(p.pair && b_mn))) p.BN = v;
+  }
   if (const char* force = getenv("NEKO_GEMM_SPLITS")) { const int v = atoi(force); if (v >= 1 && can_split) p.splits = v; }
   // rasterisation: the operand that is re-read across the concurrently running tiles should be the small one --
   // walk the shorter block dimension fastest so one wave covers a squarish patch of C and the long operand streams

@@ -63,6 +63,20 @@ def test_gemm_layouts(ops, M, N, K, a_mn, b_mn):
     assert err < tol, f"max err {err} (tol {tol})"
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("M,N,K,b_mn", [(7680, 768, 3072, False), (1000, 2304, 768, False), (640, 768, 768, True)])
+def test_gemm_tile_width_192(ops, monkeypatch, pair, M, N, K, b_mn):
+    """The 192-column tile (single CTA and CTA pair), forced through NEKO_GEMM_BN / NEKO_GEMM_PAIR."""
+    monkeypatch.setenv("NEKO_GEMM_BN", "192")
+    monkeypatch.setenv("NEKO_GEMM_PAIR", str(pair))
+    a = _rand((M, K), 61, 1.0, torch.bfloat16)
+    b = _rand((K, N) if b_mn else (N, K), 62, 0.05, torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, b_mn=b_mn, epilogue=ops.EPI_BF16, out=out)
+    ref = a.float() @ (b.float() if b_mn else b.float().t())
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(768, 768, 7680), (768, 3072, 7680), (768, 2304, 4000), (3072, 768, 15808), (256, 128, 2048)])
 def test_gemm_split_k_weight_gradients(ops, M, N, K):
     """wgrad shape: few output tiles, K = the token axis -> split-K with fp32 RED reduction, both overwrite and
