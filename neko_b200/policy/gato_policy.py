@@ -333,6 +333,7 @@ class GatoPolicy(nn.Module):
         self._params = params
         self._gview_cache = {}
         self._wview_cache = {}
+        self._grad_pairs_cache = {}
         # gradient ranges that must start from zero each step (everything except the matrices a single non-split
         # or self-zeroing wgrad GEMM overwrites)
         overwritten = {"predict_token.weight"} | {f"transformer.h.{i}.{m}.weight" for i in range(self.layers)
@@ -403,7 +404,16 @@ class GatoPolicy(nn.Module):
             self._bf16_versions = vers
 
     def zero_grad(self, set_to_none: bool = True):
-        super().zero_grad(set_to_none=set_to_none)
+        # nn.Module.zero_grad walks the module tree (named_modules / named_members, ~0.2 ms here); every parameter of this
+        # policy is in the arena table, so iterate that
+        if set_to_none:
+            for p in self._params.values():
+                p.grad = None
+        else:
+            for p in self._params.values():
+                if p.grad is not None:
+                    p.grad.detach_()
+                    p.grad.zero_()
         self._grad_live = False
 
     def _begin_grads(self, has_images: bool, zero: bool = True):
@@ -422,15 +432,22 @@ class GatoPolicy(nn.Module):
                     self._grad_arena[lo:hi].zero_()
             for n, p in self._params.items():
                 p.grad = None
-        for n, p in self._params.items():
-            if p.grad is not None or n == "transformer.wte.weight":
-                continue
-            if n.startswith("image_embedding."):
-                if not has_images or (".patch_pos_encoding." in n and not self.use_patch_pos_encoding):
+        pairs = self._grad_pairs_cache.get(has_images)
+        if pairs is None or pairs[0][1].data_ptr() != self._grad_arena.data_ptr() + 4 * self._offs[pairs[0][2]]:
+            pairs = []
+            for n, p in self._params.items():
+                if n == "transformer.wte.weight":
                     continue
-            if n == "pos_embed_observation.weight" and not self.use_pos_encoding:
-                continue
-            p.grad = self._gview(n)
+                if n.startswith("image_embedding."):
+                    if not has_images or (".patch_pos_encoding." in n and not self.use_patch_pos_encoding):
+                        continue
+                if n == "pos_embed_observation.weight" and not self.use_pos_encoding:
+                    continue
+                pairs.append((p, self._gview(n), n))
+            self._grad_pairs_cache[has_images] = pairs
+        for p, v, _n in pairs:
+            if p.grad is None:
+                p.grad = v
         self._grad_live = True
         return live
 
@@ -458,10 +475,17 @@ class GatoPolicy(nn.Module):
         self._check_arena()
         if inputs is not None:
             state = self._plan(inputs, compute_loss)
-            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values())
+            anchor = None
+            if torch.is_grad_enabled():
+                anchor = self._params["predict_token.weight"]
+                if not anchor.requires_grad:
+                    anchor = next((p for p in self._params.values() if p.requires_grad), None)
+            need_grad = anchor is not None
             state.need_grad = need_grad
             if need_grad:
-                logits, loss = _FusedStep.apply(self, state, *self._params.values())
+                # gradients are written straight into the arena behind every .grad, so the autograd node only needs ONE
+                # differentiable input to exist (handing it all ~100 parameters costs ~0.1 ms of host time per step)
+                logits, loss = _FusedStep.apply(self, state, anchor)
             else:
                 logits, loss = self._engine_forward(state)
             if not compute_loss:
