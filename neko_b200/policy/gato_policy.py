@@ -470,11 +470,31 @@ class GatoPolicy(nn.Module):
     # ------------------------------------------------------------------------------------------
     # public API
     # ------------------------------------------------------------------------------------------
+    def stage(self, inputs: list, compute_loss: bool = True):
+        """Batch producer hook: do the host half of a step ahead of time -- plan the batch (descriptors, loss
+        rows, train-mode patch bins, dropout seed) and enqueue its single pinned -> device copy -- and return a handle that
+        ``forward(handle)`` consumes.  Call it for step i+1 right after enqueueing step i's backward and before reading step
+        i's loss: the planning then overlaps the GPU work of step i.  The copy is ordered on the compute stream, so the
+        staging buffer is never overwritten under a step that is still reading it; at most ONE staged handle may be
+        outstanding."""
+        self._check_arena()
+        st = self._plan(inputs, compute_loss)
+        st.staged = True
+        return st
+
     def forward(self, inputs: Optional[list] = None, compute_loss=False, **kwargs):
-        """gato_policy.py:156-192.  Returns (logits [B,S,V] fp32, loss or None)."""
+        """gato_policy.py:156-192.  Returns (logits [B,S,V] fp32, loss or None).  ``inputs`` may also be a handle returned by
+        ``stage()``."""
         self._check_arena()
         if inputs is not None:
-            state = self._plan(inputs, compute_loss)
+            if isinstance(inputs, _State):
+                state = inputs
+                if not getattr(state, "staged", False):
+                    raise RuntimeError("forward() was given a state object that did not come from stage() (or was already used)")
+                state.staged = False
+                state.compute_loss = bool(compute_loss)
+            else:
+                state = self._plan(inputs, compute_loss)
             anchor = None
             if torch.is_grad_enabled():
                 anchor = self._params["predict_token.weight"]

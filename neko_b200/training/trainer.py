@@ -91,6 +91,8 @@ class Trainer:
         self.exp_name = exp_name
         self.steps = 0
         self.min_lr = args.learning_rate / args.min_factor
+        self.prefetch = True          # stage the next batch before reading the current loss (GatoPolicy.stage)
+        self._prefetched = None
 
     # task sampling ----------------------------------------------------------------------------------------
     def _sample(self, kind: str, n: int) -> List[dict]:
@@ -131,7 +133,8 @@ class Trainer:
         t0 = time.time()
         losses = []
         for micro in range(accum):
-            batch = self.sample_combined_batch()
+            batch = self._prefetched if self._prefetched is not None else self.sample_combined_batch()
+            self._prefetched = None
             last = micro == accum - 1
             ctx = self.sync.no_sync() if (self.sync is not None and not last) else _null()
             with ctx:
@@ -141,6 +144,9 @@ class Trainer:
         self.optimizer.step(max_norm=0.0 if a.disable_grad_clip else a.grad_norm_clip)
         self.optimizer.zero_grad()
         self.steps += 1
+        if self.prefetch and hasattr(self.model, "stage"):
+            # batch producer: sample + plan + enqueue the H2D copy of the next batch while the GPU still works on this step
+            self._prefetched = self.model.stage(self.sample_combined_batch(), compute_loss=True)
         loss_val = torch.stack(losses).mean().cpu().item()   # host sync once per step, like trainer.py:188
         return loss_val, {"training/learning_rate": self.optimizer.lr, "time/train_step": time.time() - t0}
 

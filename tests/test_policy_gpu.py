@@ -486,3 +486,32 @@ def test_kv_cached_generation_matches_full_recompute(case):
         if float(top[0] - top[1]) <= 4 * LOGIT_TOL:
             break
         assert t_kv[i] == t_full[i], i
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_staged_batches_give_the_same_step(graphs):
+    """GatoPolicy.stage(): planning + upload ahead of time, forward(handle) later -- same loss / logits / gradients as
+    forward(batch); a handle is single-use."""
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w, train=False)
+    m.use_cuda_graphs = graphs
+    batch = small_batch("mixed", cfg.text_tokens)
+    for _ in range(3 if graphs else 1):
+        m.zero_grad()
+        logits0, loss0 = m(batch, compute_loss=True)
+        loss0.backward()
+        g0 = m._grad_arena.clone()
+        l0 = logits0.clone()
+    nxt = m.stage(batch, compute_loss=True)
+    for _ in range(3):
+        cur = nxt
+        m.zero_grad()
+        logits1, loss1 = m(cur, compute_loss=True)
+        loss1.backward()
+        nxt = m.stage(batch, compute_loss=True)     # next step staged before this step's loss is read
+        assert abs(loss1.item() - loss0.item()) <= 1e-6 * abs(loss0.item())
+        assert torch.equal(logits1, l0)
+        assert (m._grad_arena - g0).abs().max().item() <= 1e-6 * max(1.0, g0.abs().max().item())
+    with pytest.raises(RuntimeError):
+        m(cur, compute_loss=True)                   # already consumed
