@@ -136,6 +136,7 @@ class _FusedStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, policy, state, *params):
         logits, loss = policy._engine_forward(state)
+        policy._bwd_pending = state.compute_loss
         ctx.policy = policy
         ctx.state = state
         ctx.n_params = len(params)
@@ -150,6 +151,7 @@ class _FusedStep(torch.autograd.Function):
     def backward(ctx, _g_logits, g_loss):
         if g_loss is None:
             return (None, None) + (None,) * ctx.n_params
+        ctx.policy._bwd_pending = False
         ctx.policy._engine_backward(ctx.state, g_loss)
         # gradients were written straight into the flat arena behind every parameter's .grad
         return (None, None) + (None,) * ctx.n_params
@@ -277,6 +279,7 @@ class GatoPolicy(nn.Module):
         self._gscale_buf = torch.ones((), dtype=torch.float32, device=dev)
         self.launches = 0
         self._drop_gen = None
+        self._bwd_pending = False       # a differentiable forward has not seen its backward yet (guards stage())
         self.use_kv_cache = True        # predict_* loops: key/value cache instead of re-running the context per token
         self._build_arena()
 
@@ -478,6 +481,9 @@ class GatoPolicy(nn.Module):
         staging buffer is never overwritten under a step that is still reading it; at most ONE staged handle may be
         outstanding."""
         self._check_arena()
+        if self._bwd_pending:
+            raise RuntimeError("stage() while a forward is waiting for its backward: the staging buffer still holds that step's "
+                               "descriptors and loss rows -- call loss.backward() first (or run the forward under torch.no_grad())")
         st = self._plan(inputs, compute_loss)
         st.staged = True
         return st
@@ -494,6 +500,7 @@ class GatoPolicy(nn.Module):
                 state.staged = False
                 state.compute_loss = bool(compute_loss)
             else:
+                self._bwd_pending = False     # a new direct forward supersedes an abandoned step
                 state = self._plan(inputs, compute_loss)
             anchor = None
             if torch.is_grad_enabled():

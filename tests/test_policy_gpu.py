@@ -515,3 +515,8 @@ def test_staged_batches_give_the_same_step(graphs):
         assert (m._grad_arena - g0).abs().max().item() <= 1e-6 * max(1.0, g0.abs().max().item())
     with pytest.raises(RuntimeError):
         m(cur, compute_loss=True)                   # already consumed
+    _, loss = m(nxt, compute_loss=True)
+    with pytest.raises(RuntimeError):
+        m.stage(batch)                              # would overwrite what the pending backward still reads
+    loss.backward()
+    m.stage(batch)
