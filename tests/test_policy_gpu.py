@@ -520,3 +520,5 @@ def test_staged_batches_give_the_same_step(graphs):
         m.stage(batch)                              # would overwrite what the pending backward still reads
     loss.backward()
     m.stage(batch)
+    with pytest.raises(RuntimeError):
+        m.stage(batch)                              # one outstanding handle at a time
