@@ -26,18 +26,30 @@ m.train()
 batch = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in s.items()} for s in bench_batch(name)]
 
 
+nxt = m.stage(batch, compute_loss=True)
+
+
 def step():
+    global nxt
     m.zero_grad()
-    _, loss = m(batch, compute_loss=True)
+    _, loss = m(nxt, compute_loss=True)
     loss.backward()
+    nxt = m.stage(batch, compute_loss=True)     # batch producer: next step planned before this loss is read
     return loss.item()
 
 
 for _ in range(5):
     step()
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(30):
+    step()
+torch.cuda.synchronize()
+print(f"unprofiled: {(time.perf_counter() - t0) / 30 * 1e3:.3f} ms/step")
 pr = cProfile.Profile()
 pr.enable()
-for _ in range(100):
+for _ in range(50):
     step()
 pr.disable()
 st = pstats.Stats(pr)
