@@ -203,3 +203,22 @@ def test_product_code_never_imports_the_oracle():
     bench = open(os.path.join(ROOT, "bench.py")).read()
     gpu_arm = bench[bench.index("def run_ours("):bench.index("def main(")]
     assert not re.search(r"^\s*(from|import)\s+oracle\b", gpu_arm, flags=re.M)   # (its cpu_baseline leg calls cpu_oracle_tokens_per_s)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON line with the contract keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "train tokens/sec (fwd+bwd)" and d["unit"] == "tokens/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["name"] == "cfg1" and "workload" in d["config"]
+    # rank != 0 of a multi-process launch exits silently
+    out2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "1"],
+                          capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert out2.returncode == 0 and "{" not in out2.stdout
