@@ -506,7 +506,11 @@ class GatoPolicy(nn.Module):
         bufs = {}
         for gi, g in enumerate(plan.image_groups):
             if g.tensors and not g.tensors[0].is_cuda:
-                bufs[gi] = self._buf(f"img_in{gi}", (g.n_frames * 3 * g.height * g.width,), torch.uint8 if g.is_u8 else torch.float32)
+                n_el, dt = g.n_frames * 3 * g.height * g.width, (torch.uint8 if g.is_u8 else torch.float32)
+                old = self._ws.get(f"img_in{gi}")
+                if old is not None and (old.numel() < n_el or old.dtype != dt) and self._copy_stream is not None:
+                    self._copy_stream.synchronize()    # the buffer is about to be replaced: no copy may still target it
+                bufs[gi] = self._buf(f"img_in{gi}", (n_el,), dt)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
