@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+tests_dir = os.path.dirname(os.path.abspath(__file__))
+if tests_dir not in sys.path:      # shared helpers (tests/_random_batches.py)
+    sys.path.insert(0, tests_dir)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 

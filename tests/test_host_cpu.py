@@ -230,36 +230,8 @@ def test_plan_matches_oracle_on_random_mixed_batches(seed):
     embeddings, continuous / discrete observations and actions, ragged lengths, with and without pad_seq): the host planner's
     loss rows, left-padding offsets, token counts and per-sample descriptor table against the oracle's tokenisation."""
     from neko_b200.policy.packing import build_plan
-    rs = np.random.RandomState(1000 + seed)
-    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
-    ctx = 160
-    pad_seq = bool(seed % 2)
-    batch = []
-    for _ in range(int(rs.randint(1, 7))):
-        kind = rs.randint(0, 6)
-        if kind == 0:
-            n = int(rs.randint(1, 40))
-            ids = rs.randint(0, 300, (n,))
-            batch.append({"text": ids.tolist() if rs.rand() < 0.5 else torch.from_numpy(ids)})
-        elif kind == 1:
-            T, o, a = int(rs.randint(1, 5)), int(rs.randint(1, 9)), int(rs.randint(1, 5))
-            batch.append({"continuous_obs": f32(rs.standard_normal((T, o)) * 3), "continuous_actions": f32(np.clip(rs.standard_normal((T, a)), -1, 1))})
-        elif kind == 2:
-            T = int(rs.randint(1, 3))
-            h, w = 16 * int(rs.randint(1, 4)), 16 * int(rs.randint(1, 3))
-            img = rs.randint(0, 256, (T, 3, h, w))
-            batch.append({"images": torch.from_numpy(img.astype(np.uint8)) if rs.rand() < 0.5 else f32(img),
-                          "discrete_actions": torch.from_numpy(rs.randint(0, 5, (T, 1)).astype(np.int32))})
-        elif kind == 3:
-            T, do = int(rs.randint(1, 5)), int(rs.randint(1, 6))
-            batch.append({"discrete_obs": torch.from_numpy(rs.randint(0, 9, (T, do)).astype(np.int64)),
-                          "continuous_actions": f32(np.clip(rs.standard_normal((T, 2)), -1, 1))})
-        elif kind == 4:
-            img = rs.randint(0, 256, (1, 3, 32, 32)).astype(np.uint8)
-            batch.append({"images": torch.from_numpy(img), "text": torch.from_numpy(rs.randint(0, 300, (int(rs.randint(1, 20)),)))})
-        else:
-            T, o = int(rs.randint(1, 4)), int(rs.randint(1, 6))
-            batch.append({"continuous_obs": f32(rs.standard_normal((T, o))), "discrete_actions": torch.from_numpy(rs.randint(0, 4, (T, 1)).astype(np.int32))})
+    from _random_batches import random_mixed_batch
+    batch, ctx, pad_seq = random_mixed_batch(seed)
     cfg = O.GatoConfig(embed_dim=32, layers=1, heads=1, context_len=ctx, text_tokens=300, pad_seq=pad_seq)
     tb = O.tokenize(batch, cfg)
     plan = build_plan(batch, patch_size=16, context_len=ctx, pad_seq=pad_seq)

@@ -522,3 +522,34 @@ def test_staged_batches_give_the_same_step(graphs):
     m.stage(batch)
     with pytest.raises(RuntimeError):
         m.stage(batch)                              # one outstanding handle at a time
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_tokenize_random_mixed_batches_bit_exact(seed):
+    """Random mixtures of every modality through the fused tokenise / embed / interleave / pad kernel: ids and both masks
+    bit-exact against the oracle, embeddings exact off the patch rows (those go through the 16-bit patch projection)."""
+    from _random_batches import random_mixed_batch
+    batch, ctx, pad_seq = random_mixed_batch(seed)
+    cfg = O.GatoConfig(embed_dim=32, layers=1, heads=1, context_len=ctx, text_tokens=300, pad_seq=pad_seq)
+    w = O.make_weights(cfg, seed=seed)
+    m = make_policy(cfg, w)
+    emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+    tb = O.tokenize(batch, cfg)
+    assert np.array_equal(tok.cpu().numpy(), tb.tokens)
+    assert np.array_equal(tm.cpu().numpy(), tb.target_masks.astype(np.float32))
+    assert np.array_equal(mk.cpu().numpy(), tb.token_masks.astype(np.float32))
+    ref = O.embed_and_interleave(batch, tb, w, cfg)
+    err = (emb.cpu() - ref).abs()
+    W = tb.tokens.shape[1]
+    S = int(max(st.ids.shape[0] for st in tb.samples))
+    is_patch = torch.zeros(tb.tokens.shape, dtype=torch.bool)
+    for b, st in enumerate(tb.samples):
+        if st.n_patches:
+            n = st.ids.shape[0]
+            pat = np.zeros(st.tokens_per_timestep, bool)
+            pat[:st.n_patches] = True
+            is_patch[b, S - n:S] = torch.from_numpy(np.tile(pat, st.n_timesteps))
+    assert float(err[~is_patch].max()) <= 1e-6
+    if is_patch.any():
+        assert float(err[is_patch].max()) <= 3e-2
+    assert W == (ctx if pad_seq and ctx > S else S)
