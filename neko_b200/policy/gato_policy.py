@@ -653,6 +653,31 @@ class GatoPolicy(nn.Module):
             n_patches = image_embeddings.shape[1]
             rows, response = [], []
             prompt = list(prompt_tokens)
+            n_ctx0 = n_patches + len(prompt)
+            if self.use_kv_cache and not self.training and n_ctx0 + max_length + 1 <= self.context_len:
+                # KV-cached variant of the loop below: the context [patches, prompt] is pushed through the decoder once (the
+                # trailing separator is causal dead weight: it never influences the positions before it), then every picked
+                # token enters as ONE new position: embed_token row + the position embedding of its slot inside the
+                # timestep's observation block (patches first, then text: gato_policy.py:380-385).
+                emb, _, _, _ = self.tokenize_input_dicts([{"image_embeddings": image_embeddings,
+                                                           "text": torch.tensor(prompt, dtype=torch.long)}])
+                cache = _KVCache(self.layers, self.context_len, self.embed_dim, self.device)
+                hf = self._decode_hidden(emb[:, :n_ctx0, :], None, kv=cache)[-1:]
+                cache.len = n_ctx0
+                cache.decoding = True
+                for idx in range(max_length):
+                    row = self._head(hf.contiguous(), 1)[0, lo:hi + 1]
+                    rows.append(row)
+                    tok = int(self._pick(row, deterministic))
+                    response.append(tok)
+                    if idx + 1 == max_length:
+                        break
+                    e = self.embed_token(torch.tensor([tok + lo], device=self.device)).reshape(1, 1, -1)
+                    if self.use_pos_encoding:
+                        e = e + self.pos_embed_observation.weight.detach()[n_ctx0 + idx]
+                    hf = self._decode_hidden(e, None, kv=cache)
+                    cache.len += 1
+                return torch.stack(rows, dim=0), self.text_tokenizer.decode(response)
             for idx in range(max_length):
                 batch = {"image_embeddings": image_embeddings, "text": torch.tensor(prompt + response, dtype=torch.long)}
                 logits, _ = self.forward([batch])

@@ -553,3 +553,38 @@ def test_tokenize_random_mixed_batches_bit_exact(seed):
     if is_patch.any():
         assert float(err[is_patch].max()) <= 3e-2
     assert W == (ctx if pad_seq and ctx > S else S)
+
+
+def test_kv_cached_image_response_matches_full_recompute():
+    """predict_answer / predict_caption through the KV cache against the reference-style loop (full context per token)."""
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=64, text_tokens=200)
+    w = O.make_weights(cfg, seed=23)
+    m = make_policy(cfg, w)
+
+    class _Txt(_Tok):
+        def decode(self, ids):
+            return " ".join(str(i) for i in ids)
+
+        def encode(self, s):
+            return [int(t) for t in s.split()]
+
+    m.text_tokenizer = _Txt(cfg.text_tokens)
+    rs = np.random.RandomState(12)
+    img = torch.from_numpy(rs.randint(0, 256, (1, 3, 32, 48)).astype(np.uint8))
+    for question, n_new in (("5 7 11 13", 6), ("", 5)):
+        outs = []
+        for use_kv in (True, False):
+            m.use_kv_cache = use_kv
+            if question:
+                logits, text = m.predict_answer(img, question, max_length=n_new, deterministic=True)
+            else:
+                logits, text = m.predict_caption(img, max_length=n_new, deterministic=True)
+            outs.append((logits.float().cpu(), [int(t) for t in text.split()]))
+        (l_kv, t_kv), (l_full, t_full) = outs
+        assert tuple(l_kv.shape) == tuple(l_full.shape) == (n_new, cfg.text_tokens)
+        for i in range(n_new):
+            assert (l_kv[i] - l_full[i]).abs().max().item() <= LOGIT_TOL, (question, i)
+            top = torch.topk(l_full[i], 2).values
+            if float(top[0] - top[1]) <= 4 * LOGIT_TOL:
+                break
+            assert t_kv[i] == t_full[i], (question, i)
