@@ -11,7 +11,7 @@ import json
 import math
 import os
 import time
-from typing import List, Sequence
+from typing import Optional, List, Sequence
 
 import torch
 
@@ -83,6 +83,23 @@ class FusedAdamW:
 
     def zero_grad(self):
         self.policy.zero_grad()
+
+    # optimiser state for checkpoint / resume (the reference saves the model only, utils/utils.py:19-32)
+    def state_dict(self):
+        p = self.policy
+        return {"t": self.t, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                "exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                "layout": {n: (int(p._offs[n]), tuple(q.shape)) for n, q in p._params.items()}}
+
+    def load_state_dict(self, sd):
+        p = self.policy
+        layout = {n: (int(p._offs[n]), tuple(q.shape)) for n, q in p._params.items()}
+        if sd["layout"] != layout:
+            raise ValueError("optimizer state was saved for a different parameter layout (model configuration)")
+        self.t, self.lr = int(sd["t"]), float(sd["lr"])
+        self.betas, self.eps, self.weight_decay = tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
 
 
 class Trainer:
@@ -166,11 +183,28 @@ class _null:
         return False
 
 
-def save_checkpoint(model, save_dir: str, name: str, args) -> str:
-    """utils/utils.py:19-32 file layout: <save_dir>/<name>.pt (state_dict) + args.json."""
+def save_checkpoint(model, save_dir: str, name: str, args, optimizer: Optional["FusedAdamW"] = None, step: Optional[int] = None) -> str:
+    """utils/utils.py:19-32 file layout: <save_dir>/<name>.pt (state_dict, loadable by the reference) + args.json; with an
+    optimiser also <name>.optim.pt (AdamW moments, step counters) so that training can resume exactly."""
     os.makedirs(save_dir, exist_ok=True)
     path = os.path.join(save_dir, f"{name}.pt")
     torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
     with open(os.path.join(save_dir, "args.json"), "w") as f:
         json.dump({k: v for k, v in vars(args).items()}, f, indent=1, default=str)
+    if optimizer is not None:
+        torch.save({"optimizer": optimizer.state_dict(), "step": step}, os.path.join(save_dir, f"{name}.optim.pt"))
     return path
+
+
+def load_checkpoint(model, path: str, optimizer: Optional["FusedAdamW"] = None) -> Optional[int]:
+    """Inverse of save_checkpoint: strict load of the model, and of the optimiser state when <name>.optim.pt exists.
+    Returns the saved step (or None)."""
+    sd = torch.load(path, map_location=model.device)
+    model.load_state_dict(sd)
+    opt_path = path[:-3] + ".optim.pt" if path.endswith(".pt") else path + ".optim.pt"
+    step = None
+    if optimizer is not None and os.path.exists(opt_path):
+        blob = torch.load(opt_path, map_location="cpu", weights_only=False)
+        optimizer.load_state_dict(blob["optimizer"])
+        step = blob.get("step")
+    return step

@@ -58,7 +58,8 @@ def main():
             losses = [l for l, _ in out]
             print(f"iteration {it}: steps {trainer.steps} train_loss_mean {sum(losses) / len(losses):.4f} lr {out[-1][1]['training/learning_rate']:.3e}")
     if args.save_model and rank == 0:
-        save_checkpoint(model, os.path.join(args.save_dir, "neko_b200"), f"checkpoint_{trainer.steps}", args)
+        save_checkpoint(model, os.path.join(args.save_dir, "neko_b200"), f"checkpoint_{trainer.steps}", args, optimizer=opt,
+                        step=trainer.steps)
     if world > 1:
         dist.destroy_process_group()
 
