@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 constexpr int CEF_THREADS = 1024;
 
+__device__ __forceinline__ void cef_cp_async16(void* smem_dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cef_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cef_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ float cef_block_reduce(float v, bool is_max, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -149,20 +155,31 @@ __global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_kernel(const float* _
   __shared__ float red[CEF_THREADS / 32];
   const int nv = V >> 2;
   const float inv_n = 1.0f / (float)n_rows;
+  float4* s4 = reinterpret_cast<float4*>(cef_row);
+  // Every thread owns the float4 slots tid, tid + 1024, ... of the row buffer through all passes, so the buffer needs no
+  // block-wide hand-over: a slot is refilled with the NEXT row (cp.async, 16 B, L2 only) right after its gradient has been
+  // written, and the next row's HBM read overlaps this row's gradient write instead of following it.
+  auto row_src = [&](int r) { return logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : (long long)rows[r]) * ld; };
+  if (blockIdx.x < n_rows) {
+    const float4* z4 = reinterpret_cast<const float4*>(row_src(blockIdx.x));
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) cef_cp_async16(s4 + i, z4 + i);
+    cef_cp_async_commit();
+  }
   for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
     const long long pos = rows[r];
-    const float* z = logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : pos) * ld;
+    const float* z = row_src(r);
     bf16* dz = dlogits + ((flags & NEKO_CE_DLOGITS_COMPACT) ? (long long)r : pos) * ldd;
-    // pass 1: HBM -> shared memory, running maximum
+    const bool has_next = r + (int)gridDim.x < n_rows;
+    const float4* zn4 = reinterpret_cast<const float4*>(has_next ? row_src(r + (int)gridDim.x) : z);
+    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) cef_row[i] = z[i];
+    cef_cp_async_wait_all();
+    // pass 1 (shared memory): maximum
     float mx = -INFINITY;
-    const float4* z4 = reinterpret_cast<const float4*>(z);
-    float4* s4 = reinterpret_cast<float4*>(cef_row);
     for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
-      const float4 v = __ldg(z4 + i);
-      s4[i] = v;
+      const float4 v = s4[i];
       mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
     }
-    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) { const float v = z[i]; cef_row[i] = v; mx = fmaxf(mx, v); }
+    for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) mx = fmaxf(mx, cef_row[i]);
     mx = cef_block_reduce(mx, true, red);
     // pass 2 (shared memory): e = exp(z - max), sum
     float sum = 0.f;
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_kernel(const float* _
       row_lse[r] = lse;
       row_loss[r] = (tgt >= 0 && tgt < V) ? lse - z[tgt] : 0.f;
     }
-    // pass 3 (shared memory -> HBM): (softmax - onehot) / n_rows as bf16
+    // pass 3 (shared memory -> HBM): (softmax - onehot) / n_rows as bf16; each consumed slot starts loading the next row
     const float sc = inv_n / sum;
     uint2* d2 = reinterpret_cast<uint2*>(dz);
     for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
@@ -188,11 +205,12 @@ __global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_kernel(const float* _
       const int c = i << 2;
       d2[i] = make_uint2(pack_bf16x2(v.x * sc - (c == tgt ? inv_n : 0.f), v.y * sc - (c + 1 == tgt ? inv_n : 0.f)),
                          pack_bf16x2(v.z * sc - (c + 2 == tgt ? inv_n : 0.f), v.w * sc - (c + 3 == tgt ? inv_n : 0.f)));
+      if (has_next) cef_cp_async16(s4 + i, zn4 + i);   // after the value above has been consumed (same thread, same slot)
     }
+    cef_cp_async_commit();
     for (int i = (nv << 2) + threadIdx.x; i < V; i += CEF_THREADS) dz[i] = __float2bfloat16_rn(cef_row[i] * sc - (i == tgt ? inv_n : 0.f));
     if (flags & NEKO_CE_ZERO_PAD)
       for (long long i = V + threadIdx.x; i < ldd; i += CEF_THREADS) dz[i] = __float2bfloat16_rn(0.f);
-    __syncthreads();   // the row buffer is reused by the next row
   }
 }
 
