@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert _lib.load().neko_version() >= 100
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md's call-site table must cover the whole C ABI (and name nothing that does not exist)."""
+    import re
+    from neko_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = set(_lib.declared_symbols())
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"entry points absent from INTEGRATION.md: {missing}"
+    types = {"neko_gemm_desc", "neko_dropout", "neko_b200"}
+    unknown = sorted(w for w in set(re.findall(r"`(neko_[a-z0-9_]+)`", doc)) if w not in names and w not in types)
+    assert not unknown, f"INTEGRATION.md names entry points the header does not declare: {unknown}"
+
+
 def test_struct_layouts_match_header(tmp_path):
     """ctypes mirrors vs the C header, as a C compiler lays the structs out."""
     import subprocess
