@@ -12,6 +12,8 @@ OUTPUTS.  What is recorded:
                       for the five BASELINE.json configs at the real vocabulary (50257+1024+1024).
   fwd_<case>.npz      forward(inputs, compute_loss=True) + backward on small models: loss, logits
                       and token-embedding samples, per-parameter gradient norms and samples.
+  scale_<cfg>.npz     the same record for the five BASELINE.json configs AT MODEL SCALE (d=768 / L=6 / H=24 and the
+                      real 52 305-row vocabulary; cfg1 d=128 / L=3 / H=1) on a reduced batch (``SCALE_BATCH``).
 """
 from __future__ import annotations
 
@@ -138,6 +140,64 @@ def small_batch(case: str, text_vocab: int) -> list:
     return batch
 
 
+# model-scale parity cases: BASELINE.json configuration -> samples in the reduced batch (cfg5: one sample of each kind --
+# text 1023 ids, caption 224x224 uint8 + 32 ids, VQA + 24 ids, HalfCheetah-shaped T=42, Breakout-shaped T=26)
+SCALE_BATCH = {"cfg1": 4, "cfg2": 6, "cfg3": 2, "cfg4": 2, "cfg5": 5}
+SCALE_MODES = {"cfg1": ("eval",), "cfg2": ("eval",), "cfg3": ("eval", "train"), "cfg4": ("eval",), "cfg5": ("eval",)}
+
+
+def scale_batch(name: str) -> list:
+    return O.synth_batch(name, seed=1234, batch=SCALE_BATCH[name])
+
+
+def _record(m, batch, cfg, n_logit_samples=6000):
+    """forward + backward of the reference on `batch`; the fixture keeps outputs only."""
+    torch.manual_seed(77)  # train mode: PatchPosEncoding draws from the global CPU RNG
+    m.zero_grad()
+    logits, loss = m(batch, compute_loss=True)
+    loss.backward()
+    torch.manual_seed(77)
+    with torch.no_grad():
+        emb, tok, tm, mk = m.tokenize_input_dicts(batch)
+    rs = np.random.RandomState(99)
+    B, S, V = logits.shape
+    n = n_logit_samples
+    li = np.stack([rs.randint(0, B, n), rs.randint(0, S, n), rs.randint(0, V, n)], 1)
+    ei = np.stack([rs.randint(0, B, n), rs.randint(0, S, n), rs.randint(0, cfg.embed_dim, n)], 1)
+    rec = dict(loss=np.float64(loss.item()), tokens=tok.numpy(), target_masks=tm.numpy(),
+               token_masks=mk.numpy(), logit_idx=li,
+               logit_val=logits.detach().numpy()[li[:, 0], li[:, 1], li[:, 2]],
+               emb_idx=ei, emb_val=emb.numpy()[ei[:, 0], ei[:, 1], ei[:, 2]],
+               logits_rowsum=logits.detach().numpy().sum(-1))
+    for pn, p in m.named_parameters():
+        if p.grad is None:
+            rec["gnone." + pn] = np.zeros(1)
+            continue
+        g = p.grad.numpy().reshape(-1)
+        idx = rs.randint(0, g.shape[0], min(256, g.shape[0]))
+        rec["gnorm." + pn] = np.float64(np.linalg.norm(g.astype(np.float64)))
+        rec["gidx." + pn] = idx
+        rec["gval." + pn] = g[idx]
+    return rec, logits, loss
+
+
+def gen_fwd_scale(only=None):
+    for name in SCALE_BATCH:
+        if only and name not in only:
+            continue
+        cfg = O.GatoConfig(**O.CONFIGS[name])
+        w = O.make_weights(cfg, seed=0, perturb=False)   # the reference's init distributions (zeros / ones where it has them)
+        for mode in SCALE_MODES[name]:
+            m = _ref_model(cfg, w, train=(mode == "train"))
+            rec, logits, loss = _record(m, scale_batch(name), cfg)
+            rec["tokens"] = rec["tokens"].astype(np.int32)
+            rec["target_masks"] = rec["target_masks"].astype(np.uint8)
+            rec["token_masks"] = rec["token_masks"].astype(np.uint8)
+            np.savez_compressed(os.path.join(GOLD, f"scale_{name}_{mode}.npz"), **rec)
+            print("scale", name, mode, tuple(logits.shape), float(loss), flush=True)
+            del m, logits, loss, rec
+
+
 def gen_fwd_small():
     for case, spec in SMALL_CASES.items():
         cfg = O.GatoConfig(**spec["cfg"])
@@ -178,9 +238,13 @@ def gen_fwd_small():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "scale":
+        gen_fwd_scale(sys.argv[2:] or None)
+        return
     gen_tokenizer_kat()
     gen_tok_configs()
     gen_fwd_small()
+    gen_fwd_scale()
 
 
 if __name__ == "__main__":

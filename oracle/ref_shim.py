@@ -4,7 +4,9 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``neko_b200/``) imports 
 It exists so that (1) ``oracle/make_golden.py`` can run the real reference on seeded inputs and
 write the fixtures under ``tests/golden/`` and (2) ``tests/test_oracle_vs_reference.py`` can
 pin the restatement in ``oracle/gato_oracle.py`` against the reference whenever
-``/root/reference`` is mounted (it is NOT mounted on the GPU box).
+``/root/reference`` is mounted (it is NOT mounted on the GPU box) and (3) ``bench.py --impl reference`` /
+``cpu_baseline`` can time the reference's own CPU path on the GPU box from the git-ignored copy that
+``oracle/build_ref.py`` places under ``oracle/_ref/``.
 
 The reference was written for transformers 4.30.2 / torch 2.0.1 (``env.yml:8-36``); this image
 has transformers 5.x and lacks gymnasium, so a handful of in-memory shims are installed before
@@ -17,11 +19,31 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("NEKO_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+VENDORED_ROOT = os.path.join(_HERE, "_ref")     # written by oracle/build_ref.py (git-ignored; travels to the GPU box)
+
+
+def _find_root() -> str:
+    """The mounted reference if there is one, else the copy oracle/build_ref.py placed under oracle/_ref/."""
+    cands = [os.environ.get("NEKO_REFERENCE_ROOT"), "/root/reference", VENDORED_ROOT]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "gato", "policy", "gato_policy.py")):
+            return c
+    return os.environ.get("NEKO_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "gato", "policy", "gato_policy.py"))
+
+
+def reference_kind() -> str:
+    """'mounted' (/root/reference), 'vendored' (oracle/_ref) or 'absent'."""
+    if not reference_available():
+        return "absent"
+    return "vendored" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(VENDORED_ROOT) else "mounted"
 
 
 class _FakeTextTokenizer:
