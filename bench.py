@@ -81,46 +81,81 @@ def model_flops_per_step(cfg, N, S):
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port): used for cpu_baseline and for --impl reference
 # ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_tokens_per_s(config: str, sample_batch: int, steps: int, warmup: int):
+def _cpu_step_fn(config: str, n_samples):
+    """(step(), tokens per step, kind, n_samples).  kind "reference": the UNMODIFIED reference (GatoPolicy of
+    gato/policy/gato_policy.py, imported from /root/reference or from the git-ignored copy oracle/build_ref.py placed under
+    oracle/_ref/, through the in-memory shims of oracle/ref_shim.py) -- model(batch, compute_loss=True); loss.backward() on
+    the host cores, fp32, dropout 0.  kind "port": the oracle restatement, only when no reference tree is present."""
     from oracle import gato_oracle as O
+    from oracle import ref_shim
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = O.GatoConfig(**O.CONFIGS[config])
     w = O.make_weights(cfg, seed=0, perturb=False)
+    batch = O.synth_batch(config, seed=1234, batch=n_samples)
+    tokens = int(O.tokenize(batch, cfg).token_masks.sum())
+    if ref_shim.reference_available():
+        ref_shim.set_text_vocab(cfg.text_tokens)
+        G = ref_shim.load_reference_policy_class()
+        m = G(device="cpu", embed_dim=cfg.embed_dim, layers=cfg.layers, heads=cfg.heads, dropout=0.0, resid_mid_channels=128,
+              context_len=cfg.context_len)
+        m.transformer.drop.p = 0.0
+        m.load_state_dict(w, strict=False)
+        m.train()
+
+        def step():
+            m.zero_grad(set_to_none=True)
+            _logits, loss = m(batch, compute_loss=True)
+            loss.backward()
+            return float(loss.detach())
+        return step, tokens, "reference", len(batch)
     for t in w.values():
         t.requires_grad_(True)
-    batch = O.synth_batch(config, seed=1234, batch=sample_batch)
-    tokens = int(O.tokenize(batch, cfg).token_masks.sum())
-    times = []
-    for i in range(warmup + steps):
+
+    def step():
         for t in w.values():
             t.grad = None
-        t0 = time.perf_counter()
         out = O.forward(w, batch, cfg, compute_loss=True)
         out.loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return tokens / (sum(times) / len(times)), tokens, sum(times) / len(times)
+        return float(out.loss.detach())
+    return step, tokens, "port", len(batch)
+
+
+def cpu_tokens_per_s(config: str, n_samples, steps: int, warmup: int, budget_s: float):
+    """Times the CPU arm: `warmup` untimed steps, then up to `steps` timed ones, stopping early once `budget_s` seconds of
+    timed work are spent (at least one timed step)."""
+    step, tokens, kind, nb = _cpu_step_fn(config, n_samples)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if sum(times) >= budget_s:
+            break
+    sec = sum(times) / len(times)
+    return tokens / sec, tokens, sec, kind, nb, len(times)
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path (the oracle port: /root/reference is not on the GPU box)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, on the FULL batch of
+    the configuration (oracle port on the same batch only if no reference tree is present)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
-    # every step is a bounded sample of the workload (a few samples of the batch, ~0.3-1 s of CPU work); K and W are
-    # honoured up to a cap that keeps the whole run within a couple of minutes
-    steps, warm = max(1, min(args.steps, 60)), max(1, min(args.warmup, 5))
-    tps, tokens, sec = cpu_oracle_tokens_per_s(args.config, sample, steps, warm)
+    # K and W are honoured up to a time budget that keeps the whole run within a few minutes (one full-batch fwd+bwd is
+    # 2-30 s of CPU work depending on the configuration)
+    tps, tokens, sec, kind, nb, done = cpu_tokens_per_s(args.config, None, max(1, args.steps), max(1, min(args.warmup, 2)), 150.0)
     cores = os.cpu_count() or 1
-    desc = (f"fwd+bwd over {sample} samples of the {args.config} batch ({tokens} tokens) per step, fp32 torch-CPU, {cores} threads, "
-            f"{steps} timed steps after {warm} warm-up")
+    desc = (f"fwd+bwd over the full {args.config} batch ({nb} samples, {tokens} tokens) per step, fp32 torch-CPU, {cores} threads, "
+            f"{done} timed steps (time-capped) after {max(1, min(args.warmup, 2))} warm-up; "
+            + ("unmodified reference GatoPolicy from oracle/_ref or /root/reference" if kind == "reference" else "oracle port (no reference tree present)"))
     print(json.dumps({
         "impl": "reference", "metric": "train tokens/sec (fwd+bwd)", "value": round(tps, 2), "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOADS[args.config], "name": args.config},
-        "cpu_baseline": {"value": round(tps, 2), "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+        "steps": done, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "name": args.config, "tokens_per_step_per_gpu": tokens, "same_config": True},
+        "cpu_baseline": {"value": round(tps, 2), "unit": "tokens/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": round(tps, 2), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -460,11 +495,13 @@ def run_ours(args):
     if world == 1 and not args.no_front_end:
         out["front_end"] = front_end_roofline(model, host_batch, dev, cfgd, args.config)
     if world == 1 and not args.no_cpu_baseline:
-        sample = {"cfg1": 4, "cfg2": 4, "cfg3": 2, "cfg4": 2, "cfg5": 4}[args.config]
-        ctps, ctok, csec = cpu_oracle_tokens_per_s(args.config, sample, 2, 1)
-        out["cpu_baseline"] = {"value": round(ctps, 2), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
-                               "sample": f"2 timed fwd+bwd steps over {sample} samples of the {args.config} batch ({ctok} tokens/step, "
-                                         f"{csec:.2f} s/step), fp32 torch-CPU oracle port"}
+        # bounded sample: the first samples of the same batch, ~10-30 s of CPU work in total
+        sample = {"cfg1": 4, "cfg2": 8, "cfg3": 4, "cfg4": 2, "cfg5": 5}[args.config]
+        ctps, ctok, csec, kind, nb, done = cpu_tokens_per_s(args.config, sample, 3, 1, 20.0)
+        out["cpu_baseline"] = {"value": round(ctps, 2), "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": kind,
+                               "sample": f"{done} timed fwd+bwd steps over {nb} samples of the {args.config} batch ({ctok} tokens/step, "
+                                         f"{csec:.2f} s/step), fp32 torch-CPU, "
+                                         + ("unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port")}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

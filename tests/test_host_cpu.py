@@ -215,7 +215,7 @@ def test_product_code_never_imports_the_oracle():
     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M)
     bench = open(os.path.join(ROOT, "bench.py")).read()
     gpu_arm = bench[bench.index("def run_ours("):bench.index("def main(")]
-    assert not re.search(r"^\s*(from|import)\s+oracle\b", gpu_arm, flags=re.M)   # (its cpu_baseline leg calls cpu_oracle_tokens_per_s)
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", gpu_arm, flags=re.M)   # (its cpu_baseline leg calls cpu_tokens_per_s)
 
 
 def test_bench_reference_arm_prints_the_contract_line():
@@ -228,7 +228,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(line)
     assert d["impl"] == "reference" and d["metric"] == "train tokens/sec (fwd+bwd)" and d["unit"] == "tokens/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_shim
+    # the reference itself whenever a tree is present (/root/reference here, oracle/_ref on the GPU box), else the port
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["same_config"] is True and d["config"]["tokens_per_step_per_gpu"] == 960   # the FULL cfg1 batch
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["name"] == "cfg1" and "workload" in d["config"]
     # rank != 0 of a multi-process launch exits silently
@@ -259,3 +263,25 @@ def test_plan_matches_oracle_on_random_mixed_batches(seed):
     for b, st in enumerate(tb.samples):
         assert desc[b, 0] == st.n_timesteps and desc[b, 1] == st.n_patches
         assert desc[b, 0] * (desc[b, 1:7].sum() + 1) == st.ids.shape[0]
+
+
+def test_vendored_reference_recipe(tmp_path):
+    """oracle/build_ref.py: the copy under oracle/_ref/ is byte-identical to the mounted reference's path files and imports
+    through the shims (what bench.py --impl reference uses on the GPU box)."""
+    import hashlib
+    from oracle import build_ref, ref_shim
+    if not os.path.isdir("/root/reference/gato"):
+        pytest.skip("no /root/reference in this container")
+    assert build_ref.build()
+    for rel in build_ref.FILES:
+        src = os.path.join("/root/reference", rel)
+        if os.path.exists(src):
+            assert hashlib.sha256(open(src, "rb").read()).digest() == hashlib.sha256(open(os.path.join(build_ref.DST, rel), "rb").read()).digest(), rel
+    code = ("from oracle import ref_shim; assert ref_shim.reference_kind() == 'vendored', ref_shim.REFERENCE_ROOT; "
+            "G = ref_shim.load_reference_policy_class(); "
+            "m = G(device='cpu', embed_dim=32, layers=1, heads=1, dropout=0.0, resid_mid_channels=128, context_len=32); print('ok')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, NEKO_REFERENCE_ROOT=build_ref.DST))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
+    # oracle/_ref must stay out of the history
+    assert "oracle/_ref/" in open(os.path.join(ROOT, ".gitignore")).read()
