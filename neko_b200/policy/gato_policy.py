@@ -539,6 +539,10 @@ class GatoPolicy(nn.Module):
                     raise RuntimeError("forward() was given a state object that did not come from stage() (or was already used)")
                 state.staged = False
                 state.compute_loss = bool(compute_loss)
+                if state.stager_gen != self._stager.generation:
+                    # another batch went through the (single, pointer-stable) staging buffer after stage(): an evaluation
+                    # forward, tokenize_input_dicts, predict_*.  Upload the staged plan again -- same layout, same seed.
+                    self._upload_plan(state, state.drop_seed_host)
             else:
                 self._bwd_pending = False     # a new direct forward supersedes an abandoned step
                 state = self._plan(inputs, compute_loss)
@@ -746,12 +750,19 @@ class GatoPolicy(nn.Module):
                 rb[off:off + T * n_h * n_w] = np.tile(np.repeat(hp.numpy(), n_w), T)
                 cb[off:off + T * n_h * n_w] = np.tile(np.tile(wp.numpy(), n_h), T)
             st.row_bins, st.col_bins = rb, cb
-        descs, fv, iv, first_valid, loss_rows, h2d, hdr = self._stager.upload(plan, self._next_drop_seed())
+        st.h2d_bytes = 0
+        self._upload_plan(st, self._next_drop_seed())
+        return st
+
+    def _upload_plan(self, st: _State, seed):
+        """The batch's single pinned -> device copy (descriptors, scalars, ids, loss rows, dropout seed header)."""
+        descs, fv, iv, first_valid, loss_rows, h2d, hdr = self._stager.upload(st.plan, seed)
         st.descs, st.fvals, st.ivals, st.first_valid, st.loss_rows = descs, fv, iv, first_valid, loss_rows
         st.drop_seed = hdr[:2]
-        self._last_drop = (st.drop_seed, plan.B, plan.width)
-        st.h2d_bytes = h2d
-        return st
+        st.drop_seed_host = seed
+        st.stager_gen = self._stager.generation
+        self._last_drop = (st.drop_seed, st.plan.B, st.plan.width)
+        st.h2d_bytes += h2d
 
     def _tok_params(self, plan: BatchPlan) -> TokParams:
         return TokParams(mu=float(self.mu), M=float(self.M), n_bins=int(self.continuous_tokens),

@@ -234,6 +234,7 @@ class Stager:
         self._next = 0
         self._pinned: Optional[torch.Tensor] = None
         self._dev: Optional[torch.Tensor] = None
+        self.generation = 0      # bumped by every upload: a staged batch knows whether the device buffer still holds it
 
     def _ensure(self, nbytes: int):
         if self._dev is None or self._dev.numel() < nbytes:
@@ -298,6 +299,7 @@ class Stager:
             if not host_i and plan.n_i:
                 torch.cat([t.to(self.device) for t in plan.ivals], out=view(2, torch.int32))
         self._event.record(torch.cuda.current_stream(self.device))
+        self.generation += 1
         descs = dev[offs[0]:offs[0] + sizes[0]]
         fv = view(1, torch.float32)
         iv = view(2, torch.int32)

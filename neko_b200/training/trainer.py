@@ -50,7 +50,11 @@ def lr_at_step(step: int, *, warmup_steps: int, training_steps: int, base_lr: fl
 
 
 class FusedAdamW:
-    """AdamW + global-norm clip over the policy's flat arenas: two launches per step (sum of squares, update)."""
+    """AdamW + global-norm clip over the policy's flat arenas: one sum-of-squares launch plus one update launch per
+    contiguous run of LIVE parameters.  Like torch.optim.AdamW under ``zero_grad(set_to_none=True)`` (what the reference
+    runs, train.py:127-133 / trainer.py:186), a parameter whose ``.grad`` is None this cycle is skipped entirely -- no weight
+    decay, no moment decay, no step-count increment: ``transformer.wte`` always, the image stack on image-free batches, the
+    position tables when disabled, anything frozen.  Step counts (bias correction) are therefore per parameter."""
 
     def __init__(self, policy, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1):
         self.policy = policy
@@ -58,13 +62,34 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(policy._param_arena)
         self.exp_avg_sq = torch.zeros_like(policy._param_arena)
         self.sumsq = torch.zeros((), device=policy._param_arena.device)
-        self.t = 0
+        self.t = 0              # optimiser steps taken
+        self.steps = {}         # per-parameter update count (torch's state['step'])
+
+    def _live_runs(self):
+        """[lo, hi, step] arena ranges of the parameters that have a gradient, merged where adjacent with equal counts."""
+        p = self.policy
+        total = p._param_arena.numel()
+        order = p._order
+        runs = []
+        for k, n in enumerate(order):
+            if p._params[n].grad is None:
+                continue
+            lo = p._offs[n]
+            hi = p._offs[order[k + 1]] if k + 1 < len(order) else total
+            t = self.steps[n] = self.steps.get(n, 0) + 1
+            if runs and runs[-1][1] == lo and runs[-1][2] == t:
+                runs[-1][1] = hi
+            else:
+                runs.append([lo, hi, t])
+        return runs
 
     def step(self, max_norm: float = 0.0, grad_div: float = 1.0):
         p = self.policy
         self.t += 1
         ss = None
         if max_norm > 0:
+            # ranges without a gradient hold zeros (GatoPolicy._begin_grads clears them each cycle): the norm over the whole
+            # arena equals clip_grad_norm_ over the parameters that have one
             self.sumsq.zero_()
             ops.sumsq(p._grad_arena, self.sumsq)
             ss = self.sumsq
@@ -74,9 +99,13 @@ class FusedAdamW:
         w16 = p._w16_arena if dual else None
         wbf = p._wbf_arena if dual else (p._w16_arena if p._w16_arena.dtype == torch.bfloat16 and p.fwd_dtype == torch.bfloat16 else None)
         fused = (w16 is not None) or (wbf is not None)
-        ops.adamw_step(p._param_arena, p._grad_arena, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                       self.eps, self.weight_decay, self.t, ss, max_norm, grad_div, w_f16=w16, w_bf16=wbf,
-                       n_cast=p._cast_end if fused else 0)
+        cast_end = p._cast_end if fused else 0
+        for lo, hi, t in self._live_runs():
+            nc = max(0, min(hi, cast_end) - lo)
+            ops.adamw_step(p._param_arena[lo:hi], p._grad_arena[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr,
+                           self.betas[0], self.betas[1], self.eps, self.weight_decay, t, ss, max_norm, grad_div,
+                           w_f16=w16[lo:] if (w16 is not None and nc) else None, w_bf16=wbf[lo:] if (wbf is not None and nc) else None,
+                           n_cast=nc)
         # the arena was updated in place by raw pointers (no torch version bump): either the copies are fresh (fused) and
         # the recorded versions stay valid, or they must be re-cast by the next forward
         p._bf16_versions = tuple(q._version for q in p._params.values()) if fused else None
@@ -87,7 +116,7 @@ class FusedAdamW:
     # optimiser state for checkpoint / resume (the reference saves the model only, utils/utils.py:19-32)
     def state_dict(self):
         p = self.policy
-        return {"t": self.t, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+        return {"t": self.t, "steps": dict(self.steps), "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
                 "exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
                 "layout": {n: (int(p._offs[n]), tuple(q.shape)) for n, q in p._params.items()}}
 
@@ -97,6 +126,7 @@ class FusedAdamW:
         if sd["layout"] != layout:
             raise ValueError("optimizer state was saved for a different parameter layout (model configuration)")
         self.t, self.lr = int(sd["t"]), float(sd["lr"])
+        self.steps = {n: int(v) for n, v in sd["steps"].items()} if "steps" in sd else {n: self.t for n in layout}
         self.betas, self.eps, self.weight_decay = tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
@@ -157,7 +187,7 @@ class Trainer:
             with ctx:
                 _, loss = self.model.forward(inputs=batch, compute_loss=True)
                 (loss / accum).backward()
-            losses.append(loss.detach())
+            losses.append(loss.detach().clone())   # graph replays return the same pooled tensor every time
         self.optimizer.step(max_norm=0.0 if a.disable_grad_clip else a.grad_norm_clip)
         self.optimizer.zero_grad()
         self.steps += 1

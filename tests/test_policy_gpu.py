@@ -235,6 +235,57 @@ def test_state_dict_layout_and_errors():
         GatoPolicy(device="cpu", embed_dim=64, layers=1, heads=2, dropout=0.0, resid_mid_channels=128)
 
 
+def test_init_distributions_match_reference():
+    """SURVEY a12 (trajectory_gpt2.py:375-386 + torch defaults for everything GatoPolicy owns): per-tensor mean / std / range
+    of a freshly constructed policy against the reference constructed on the CPU (oracle/_ref or /root/reference through the
+    shims), or against the documented distributions when no reference tree is present."""
+    from neko_b200.policy import GatoPolicy
+    from oracle import ref_shim
+    kw = dict(embed_dim=256, layers=2, heads=8, dropout=0.0, resid_mid_channels=128, context_len=128)
+    torch.manual_seed(5)
+    m = GatoPolicy(device="cuda", text_tokenizer=_Tok(50257), **kw)
+    ours = {n: p.detach().float().cpu() for n, p in m.named_parameters()}
+    ref = None
+    if ref_shim.reference_available():
+        ref_shim.set_text_vocab(50257)
+        torch.manual_seed(5)
+        r = ref_shim.load_reference_policy_class()(device="cpu", **kw)
+        ref = {n: p.detach().float() for n, p in r.named_parameters()}
+        assert set(ref) == set(ours)
+    for n, t in ours.items():
+        numel = t.numel()
+        if ref is not None:
+            q = ref[n]
+            assert tuple(q.shape) == tuple(t.shape), n
+            mean_r, std_r, lo_r, hi_r = float(q.mean()), float(q.std()) if numel > 1 else 0.0, float(q.min()), float(q.max())
+        else:   # documented distributions
+            if ".ln_" in n or "ln_f" in n or "gn2" in n:
+                mean_r, std_r = (1.0, 0.0) if n.endswith("weight") else (0.0, 0.0)
+            elif n.startswith("transformer.") and n.endswith("bias") or n == "separator_token":
+                mean_r, std_r = 0.0, 0.0
+            elif n.startswith("transformer."):
+                mean_r, std_r = 0.0, 0.02
+            elif n.endswith("embedding.weight") or n in ("embed_token.weight", "pos_embed_observation.weight"):
+                mean_r, std_r = 0.0, 1.0
+            else:
+                continue
+            lo_r = hi_r = None
+        mean_o, std_o = float(t.mean()), float(t.std()) if numel > 1 else 0.0
+        if std_r == 0.0:      # constants: ones / zeros exactly
+            assert std_o == 0.0 and mean_o == mean_r, (n, mean_o, std_o)
+            continue
+        if numel < 64:   # too few draws for moments (conv2.bias has 3): inside the kaiming-uniform support 1/sqrt(fan_in)
+            wshape = ours[n[:-4] + "weight"].shape
+            assert float(t.abs().max()) <= 1.0 / (float(np.prod(wshape[1:])) ** 0.5) + 1e-7, n
+            continue
+        se = std_r / (numel ** 0.5)
+        assert abs(mean_o - mean_r) <= 6 * se * 2 ** 0.5 + 1e-7, (n, mean_o, mean_r)
+        assert abs(std_o - std_r) <= 6 * std_r / (2 * numel) ** 0.5 * 2 ** 0.5 + 0.02 * std_r, (n, std_o, std_r)
+        if lo_r is not None and not (n.endswith("embedding.weight") or "embed" in n or n.startswith("transformer.")):
+            # uniform kaiming ranges (nn.Linear / nn.Conv2d defaults): same support
+            assert abs(float(t.min()) - lo_r) <= 0.05 * (hi_r - lo_r) and abs(float(t.max()) - hi_r) <= 0.05 * (hi_r - lo_r), n
+
+
 def test_kwargs_path_matches_inputs_path():
     cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
     w = O.make_weights(cfg, seed=3)
@@ -568,6 +619,36 @@ def test_staged_batches_give_the_same_step(graphs):
     m.stage(batch)
     with pytest.raises(RuntimeError):
         m.stage(batch)                              # one outstanding handle at a time
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_staged_batch_survives_other_forwards(graphs):
+    """stage(A); then an evaluation forward / tokenize_input_dicts / predict_* on OTHER batches (what the reference loop does
+    every log_eval_freq steps) reuses the single staging buffer; forward(handleA) must still run batch A."""
+    cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
+    w = O.make_weights(cfg, seed=3)
+    m = make_policy(cfg, w, train=False)
+    m.use_cuda_graphs = graphs
+    A = small_batch("mixed", cfg.text_tokens)
+    other = [dict(text=list(range(1, 40))), dict(continuous_obs=torch.randn(9, 4), continuous_actions=torch.rand(9, 2))]
+    for _ in range(3 if graphs else 1):
+        m.zero_grad()
+        logits0, loss0 = m(A, compute_loss=True)
+        loss0.backward()
+        g0, l0 = m._grad_arena.clone(), logits0.clone()
+    for k in range(3):
+        h = m.stage(A, compute_loss=True)
+        with torch.no_grad():
+            m(other, compute_loss=True)
+            m.tokenize_input_dicts(other[:1])
+            if k == 2:
+                m.predict_text({"text": [3, 4, 5]}, max_length=2)
+        m.zero_grad()
+        logits1, loss1 = m(h, compute_loss=True)
+        loss1.backward()
+        assert abs(loss1.item() - loss0.item()) <= 1e-6 * abs(loss0.item())
+        assert torch.equal(logits1, l0)
+        assert (m._grad_arena - g0).abs().max().item() <= 1e-6 * max(1.0, g0.abs().max().item())
 
 
 @pytest.mark.parametrize("seed", range(8))

@@ -28,17 +28,25 @@ class _Replay:
         return copy.deepcopy(b)
 
 
-def _batches(cfg, steps, seed=0):
+def _batches(cfg, steps, seed=0, images_at=()):
+    """3 control samples per step; steps listed in `images_at` swap the last one for an image-control sample, so the image
+    stack has a gradient on those steps only."""
     g = torch.Generator().manual_seed(seed)
     out = []
-    for _ in range(steps):
-        out.append([dict(continuous_obs=torch.randn(6, 5, generator=g) * 3,
-                         continuous_actions=torch.randn(6, 2, generator=g).clamp(-1, 1)) for _ in range(3)])
+    for s in range(steps):
+        b = [dict(continuous_obs=torch.randn(6, 5, generator=g) * 3,
+                  continuous_actions=torch.randn(6, 2, generator=g).clamp(-1, 1)) for _ in range(3)]
+        if s in images_at:
+            b[-1] = dict(images=torch.randint(0, 256, (3, 3, 32, 32), generator=g).float(),
+                         discrete_actions=torch.randint(0, 4, (3, 1), generator=g).to(torch.int32))
+        out.append(b)
     return out
 
 
-@pytest.mark.parametrize("lean", [True, False])
-def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
+@pytest.mark.parametrize("lean,images_at", [(True, ()), (False, ()), (True, (1, 3))])
+def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean, images_at):
+    """Against UNMODIFIED torch.optim.AdamW under zero_grad(set_to_none=True): parameters without a gradient this step
+    (transformer.wte always; the image stack on image-free steps) are skipped -- no decay, no moment update, own step count."""
     from neko_b200.policy import GatoPolicy
     from neko_b200.training.arguments import TrainingArgs
     from neko_b200.training.trainer import FusedAdamW, Trainer, lr_at_step
@@ -57,7 +65,8 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
     args.grad_norm_clip, args.disable_grad_clip = 1.0, False
     args.gradient_accumulation_steps = 1
     args.text_prop = args.caption_prop = args.vqa_prop = 0.0
-    batches = _batches(cfg, steps)
+    batches = _batches(cfg, steps, images_at=images_at)
+    m.eval()        # eval-mode patch positions (deterministic) on both sides; dropout is 0 anyway
 
     class _OneSample(_Replay):
         """Trainer draws control samples one at a time (trainer.py:211-247): hand out the batch sample by sample."""
@@ -71,7 +80,9 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
 
     opt = FusedAdamW(m, lr=args.learning_rate, betas=(args.beta_1, args.beta_2), eps=args.adam_eps, weight_decay=args.weight_decay)
     tr = Trainer(m, opt, [_OneSample(batches)], args)
-    losses = [l for l, _ in tr.train(steps)]
+    losses = []
+    for _ in range(steps):          # Trainer.train() would switch to train mode
+        losses.append(tr.train_step()[0])
 
     # reference: oracle forward/backward on CPU + torch AdamW with the same schedule and clipping
     for t in w.values():
@@ -85,13 +96,10 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
                         init_lr=args.init_lr, min_lr=args.learning_rate / args.min_factor, cosine_decay=True)
         for gI in ropt.param_groups:
             gI["lr"] = lr
-        out = O.forward(w, batches[s], cfg, compute_loss=True, training=True)
-        ropt.zero_grad()
+        out = O.forward(w, batches[s], cfg, compute_loss=True, training=False)
+        ropt.zero_grad(set_to_none=True)
         out.loss.backward()
-        for t in w.values():                      # parameters without gradient still decay in the fused arena update
-            if t.grad is None:
-                t.grad = torch.zeros_like(t)
-        torch.nn.utils.clip_grad_norm_(list(w.values()), args.grad_norm_clip)
+        torch.nn.utils.clip_grad_norm_([t for t in w.values() if t.grad is not None], args.grad_norm_clip)
         ropt.step()
         rlosses.append(float(out.loss.detach()))
     assert len(used) > 10
@@ -101,12 +109,16 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean):
     # parameters after 4 AdamW steps: updates are O(lr) per step whatever the gradient scale, so compare in units of lr
     sd = m.state_dict()
     worst = 0.0
+    w0 = O.make_weights(cfg, seed=11)
     for n, t in w.items():
-        if n == "transformer.wte.weight":
-            continue
         diff = (sd[n].detach().cpu() - t.detach()).abs()
         worst = max(worst, float(diff.mean()) / args.learning_rate)
+        if n == "transformer.wte.weight" or (n.startswith("image_embedding.") and not images_at):
+            assert torch.equal(sd[n].detach().cpu(), w0[n]), f"{n} has no gradient and must not move (no weight decay)"
     assert worst < 0.5, worst
+    if images_at:
+        assert opt.steps["image_embedding.patch_embedding.conv1.weight"] == len(images_at) and opt.steps["embed_token.weight"] == steps
+        assert "transformer.wte.weight" not in opt.steps
 
 
 def test_checkpoint_resume_is_exact(tmp_path):

@@ -95,8 +95,24 @@ if __name__ == "__main__":
         torch.cuda.synchronize()
         print("ran", name)
         sys.exit(0)
-    print(f"M={M}   us (TFLOP/s)")
-    print(f"{'call':38s}" + "".join(f"{n:>16s}" for n, _ in VARIANTS + EXTRA))
+    if os.environ.get("SWEEP_AUTO_ONLY"):
+        VARIANTS = VARIANTS[:1]
+    print(f"M={M}   us (TFLOP/s)      cuBLAS column: torch.matmul bf16 of the same M x N x K, plain bf16 output (no bias / GELU / residual)")
+    print(f"{'call':38s}" + "".join(f"{n:>16s}" for n, _ in VARIANTS + EXTRA) + f"{'cuBLAS':>16s}")
+    # the same contraction through cuBLAS (library reference, NOT on the product path): [M,K] x [K,N] bf16 -> bf16
+    SHAPES = {"qkv": (M, 3 * d, d), "attnproj": (M, d, d), "c_fc ": (M, 4 * d, d), "c_proj2  N768": (M, d, 4 * d), "dgelu": (M, 4 * d, d),
+              "d c_fc": (M, d, 4 * d), "d proj": (M, d, d), "d qkv": (M, d, 3 * d), "wgrad c_proj2": (4 * d, d, M), "wgrad c_fc": (d, 4 * d, M),
+              "wgrad proj": (d, d, M), "wgrad qkv": (d, 3 * d, M)}
+
+    def cublas_us(name):
+        for key, (m_, n_, k_) in SHAPES.items():
+            if key in name:
+                a = t((m_, k_), b16)
+                b = t((k_, n_), b16)
+                o = torch.empty(m_, n_, device=dev, dtype=b16)
+                return timeit(lambda: torch.matmul(a, b, out=o))
+        return None
+
     for name, flops, fn in cases():
         cells = []
         for _vn, env in VARIANTS + EXTRA:
@@ -109,4 +125,6 @@ if __name__ == "__main__":
             except Exception as e:  # noqa: BLE001
                 cells.append("fail")
                 print("   ", type(e).__name__, str(e)[:100])
+        cu = cublas_us(name)
+        cells.append(f"{cu:7.1f} ({flops / cu / 1e6:5.0f})" if cu else "-")
         print(f"{name:38s}" + "".join(f"{c:>16s}" for c in cells), flush=True)

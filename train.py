@@ -28,6 +28,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.manual_seed(args.seed)            # identical initial weights on every rank (and broadcast below)
     model = GatoPolicy(device=f"cuda:{local}", embed_dim=args.embed_dim, layers=args.layers, heads=args.heads, dropout=args.dropout,
                        mu=args.mu, M=args.M, activation_fn=args.activation_fn, patch_size=args.patch_size,
                        resid_mid_channels=args.resid_mid_channels, continuous_tokens=args.continuous_tokens,
@@ -36,10 +37,13 @@ def main():
                        pretrained_lm=args.pretrained_lm, flash=args.flash, tokenizer_model_name=args.tokenizer_model_name, pad_seq=args.pad_seq)
     if args.init_checkpoint:
         model.load_state_dict(torch.load(args.init_checkpoint, map_location=f"cuda:{local}"))
-    if args.dropout == 0:
-        model.transformer.drop.p = 0.0
+    # embedding dropout stays at the reference's 0.1 whatever --dropout says (GPT2Config.embd_pdrop default)
+    if args.flash and rank == 0:
+        print("--flash: no effect here -- attention never materialises the S x S scores (csrc/attention*.cu); the reference's "
+              "flag only switches its own matmul/softmax path to F.scaled_dot_product_attention (trajectory_gpt2.py:241-250)")
     model.materialize_logits = False   # the trainer discards logits (trainer.py:178)
     model.use_cuda_graphs = not args.disable_cuda_graphs
+    torch.manual_seed(args.seed + rank)     # per-rank dropout masks, patch-position draws and multinomial remainders
     sync = None
     if world > 1:
         dp.broadcast_parameters(model)
