@@ -312,7 +312,8 @@ def run_ours(args):
         # static knowledge of the task mix, as a trainer has it from --text_prop / --caption_prop / --vqa_prop
         no_text = not any(("text" in s and s["text"] is not None) for s in bench_batch(args.config, seed=0))
         bucket_mb = int(os.environ.get("NEKO_DP_BUCKET_MB", "64"))
-        sync = dp.attach(model, bucket_bytes=bucket_mb << 20, no_text_tokens=no_text)
+        sync = dp.attach(model, bucket_bytes=bucket_mb << 20, no_text_tokens=no_text, mode=os.environ.get("NEKO_DP_MODE", "overlap"),
+                         compress=os.environ.get("NEKO_DP_COMPRESS", "none"), backend=os.environ.get("NEKO_DP_BACKEND", "auto"))
     host_batch = bench_batch(args.config, seed=1234 + rank)
     dev_batch = to_device(host_batch, dev)
     pin_batch = to_pinned(host_batch)

@@ -276,6 +276,26 @@ int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     const float* grad_sumsq, float max_norm, float grad_div,
                     uint16_t* w_f16, uint16_t* w_bf16, int64_t n_cast, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient all-reduce over NVLink peer memory (replaces the DDP bucket all-reduce the reference gets from
+ * Accelerate: train.py:26-40,107; trainer.py:176-186 -- SUM over ranks, then / world).  One process per GPU; every
+ * rank's gradient arena and a small signal buffer are mapped into every process with the two ipc calls below.
+ * neko_p2p_allreduce_f32 is a two-shot, in-place, deterministic fp32 all-reduce of arena elements [lo, hi) whose CTAs
+ * (128 threads, no shared memory) are sized to co-reside with the persistent GEMM CTAs of backward; it must be
+ * called by every rank with the same (lo, hi) in the same order.  `state`: two zero-initialised uint32 words private to
+ * the rank (launch counter, CTA arrival counter) -- all barrier bookkeeping is device state, so the launch replays from a
+ * CUDA graph.  host_bufs / host_sigs are HOST arrays of `world` device pointers (index = rank, own pointers included);
+ * each signal buffer holds `world` zero-initialised uint32 words.
+ * ------------------------------------------------------------------------------------------- */
+/* Measurement aid: n_ctas CTAs of `threads` threads that idle for `ns` nanoseconds (no shared memory).  Used to queue a whole
+ * step behind a blocker so that per-kernel CUDA events see no launch gaps (bench.py), and to test which kernels co-reside. */
+int neko_debug_spin(int n_ctas, int threads, long long ns, int max_shared_carveout, void* stream);
+int neko_ipc_export(const void* dev_ptr, unsigned char* handle_out /* 64 bytes */, long long* offset_out);
+int neko_ipc_import(const unsigned char* handle /* 64 bytes */, long long offset, void** dev_ptr_out);
+int neko_ipc_close(void* dev_ptr, long long offset);
+int neko_p2p_allreduce_f32(void* const* host_bufs, void* const* host_sigs, unsigned* state, int rank, int world, long long lo,
+                           long long hi, float scale, int n_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1188,14 +1188,26 @@ class GatoPolicy(nn.Module):
             self.grad_ready_hook(lo, hi)
 
     def _engine_backward(self, st: _State, g_loss: torch.Tensor):
+        self._engine_backward_inner(st, g_loss)
+        sync = getattr(self, "_grad_sync", None)
+        if sync is not None and getattr(sync, "mode", "overlap") == "tail":
+            sync.finish_tail()
+
+    def _engine_backward_inner(self, st: _State, g_loss: torch.Tensor):
         ent = getattr(st, "graph_entry", None)
-        if ent is None or self.grad_ready_hook is not None:
+        sync = getattr(self, "_grad_sync", None)
+        hooked = self.grad_ready_hook is not None
+        # a data-parallel synchroniser whose launches are graph-safe (dp backend "p2p") is captured WITH backward: its
+        # bucket all-reduces replay on their side-stream branch of the graph
+        if ent is None or (hooked and not (sync is not None and getattr(sync, "capturable", False))):
             return self._backward_compute(st, g_loss, None)
         if st.generation != self._generation:
             raise RuntimeError("backward() called after a newer forward reused the activation workspace")
         plan = st.plan
         acc = self._begin_grads(bool(plan.n_patch_rows and getattr(st, 'img_groups', None)), zero=False)
         self._gscale_buf.copy_(g_loss.detach().to(torch.float32).reshape(()))
+        if hooked:
+            acc = (acc, bool(sync.enabled))    # no_sync() micro-steps replay a graph without the all-reduces
         gb = ent["bwd"].get(acc)
         if gb is None:
             torch.cuda.synchronize()
@@ -1204,7 +1216,7 @@ class GatoPolicy(nn.Module):
             self._capturing = True
             try:
                 with torch.cuda.graph(gph, pool=self._graph_pool):
-                    self._backward_compute(ent["state"], self._gscale_buf, acc)
+                    self._backward_compute(ent["state"], self._gscale_buf, acc[0] if isinstance(acc, tuple) else acc)
             finally:
                 self._capturing = False
             ent["bwd"][acc] = (gph, self.launches - l0)
@@ -1223,6 +1235,8 @@ class GatoPolicy(nn.Module):
         N = B * W
         n_rows = st.n_rows
         sync = getattr(self, "_grad_sync", None)
+        if sync is not None and getattr(sync, "mode", "overlap") == "tail":
+            sync = None
         if sync is not None:
             sync.begin_step()
         if acc_override is None:

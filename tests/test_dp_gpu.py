@@ -43,7 +43,8 @@ dist.all_gather(gathered, local)
 mean = torch.stack(gathered).mean(0)
 # now with the bucketed all-reduce fired from inside backward
 m.zero_grad()
-sync = dp.attach(m, bucket_bytes=1 << 16)
+sync = dp.attach(m, bucket_bytes=1 << 16, backend=os.environ["NEKO_DP_BACKEND"])
+assert sync.backend == os.environ["NEKO_DP_BACKEND"]
 _, loss = m(batch, compute_loss=True); loss.backward()
 torch.cuda.synchronize()
 err = (m._grad_arena - mean).abs().max().item()
@@ -67,7 +68,7 @@ with sync.no_sync():
     _, loss = m(ctrl, compute_loss=True); loss.backward()
 torch.cuda.synchronize()
 local_c = m._grad_arena.clone()
-sync2 = dp.attach(m, bucket_bytes=1 << 16, no_text_tokens=True)
+sync2 = dp.attach(m, bucket_bytes=1 << 16, no_text_tokens=True, backend=os.environ["NEKO_DP_BACKEND"])
 m.zero_grad()
 _, loss = m(ctrl, compute_loss=True); loss.backward()
 torch.cuda.synchronize()
@@ -81,13 +82,15 @@ print("dp ok", rank)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_dp_gradients_match_mean_of_ranks(tmp_path):
+@pytest.mark.parametrize("backend", ["p2p", "nccl"])
+def test_dp_gradients_match_mean_of_ranks(tmp_path, backend):
+    """backend p2p: the own peer-memory all-reduce kernel (csrc/p2p_allreduce.cu, the default); nccl: torch.distributed."""
     script = tmp_path / "dp_worker.py"
     script.write_text(_WORKER)
-    port = 29700 + (os.getpid() % 1000)
+    port = 29700 + (os.getpid() % 1000) + (7 if backend == "p2p" else 0)
     procs = []
     for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NEKO_ROOT=ROOT)
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NEKO_ROOT=ROOT, NEKO_DP_BACKEND=backend)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     for p in procs:
         out, _ = p.communicate(timeout=150)
