@@ -150,6 +150,7 @@ enum neko_epilogue {
 #define NEKO_GEMM_B_F16 2
 #define NEKO_GEMM_C_F16 4
 #define NEKO_GEMM_C2_F16 8
+#define NEKO_GEMM_GELU_TANH 16 /* GELU / GELU' epilogues use the tanh form (HF "gelu_new", pretrained GPT-2) instead of erf */
 
 typedef struct neko_gemm_desc {
   int32_t M, N, K;
@@ -290,11 +291,26 @@ int neko_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
 /* Measurement aid: n_ctas CTAs of `threads` threads that idle for `ns` nanoseconds (no shared memory).  Used to queue a whole
  * step behind a blocker so that per-kernel CUDA events see no launch gaps (bench.py), and to test which kernels co-reside. */
 int neko_debug_spin(int n_ctas, int threads, long long ns, int max_shared_carveout, void* stream);
+/* Device-wide shared-memory carveout preference (cudaDeviceSetCacheConfig) for kernels without one of their own: with
+ * on != 0 every kernel of the step runs in the split the all-reduce CTAs hold, so none waits for an SM to drain. */
+int neko_prefer_shared_carveout(int on);
 int neko_ipc_export(const void* dev_ptr, unsigned char* handle_out /* 64 bytes */, long long* offset_out);
 int neko_ipc_import(const unsigned char* handle /* 64 bytes */, long long offset, void** dev_ptr_out);
 int neko_ipc_close(void* dev_ptr, long long offset);
-int neko_p2p_allreduce_f32(void* const* host_bufs, void* const* host_sigs, unsigned* state, int rank, int world, long long lo,
-                           long long hi, float scale, int n_ctas, void* stream);
+/* Copy-engine flavour of the same all-reduce (what neko_b200/dp.py runs by default): NVLink traffic is moved by
+ * neko_memcpy_async between peer-mapped buffers (DMA engines, no SM), neko_p2p_signal_wait is the one-warp cross-rank
+ * barrier between the steps (signal words 32.. of the signal buffers, launch counter in state[2]) and
+ * neko_reduce_planes_f32 sums the staged contributions: dst[i] = scale * sum_q (q == self ? dst[i] : stage[q*plane+i]). */
+int neko_memcpy_async(void* dst, const void* src, long long bytes, void* stream);
+int neko_p2p_signal_wait(void* const* host_sigs, unsigned* state, int rank, int world, void* stream);
+int neko_reduce_planes_f32(float* dst, const float* stage, long long plane, int n_planes, int self, long long n, float scale, void* stream);
+/* host_stage (nullable): HOST array of `world` device pointers to every rank's staging buffer (world planes of stage_plane
+ * floats each).  When given, the exchange runs push style -- contributions are WRITTEN into the owner's staging planes
+ * at stage_off (the caller advances it by ceil((hi-lo)/world) + 4 per call within a step), reduced there, and the result is
+ * written into every arena: no loads cross NVLink.  NULL: pull style (peer loads, in place, no staging memory). */
+int neko_p2p_allreduce_f32(void* const* host_bufs, void* const* host_sigs, void* const* host_stage, long long stage_plane,
+                           long long stage_off, unsigned* state, int rank, int world, long long lo, long long hi, float scale,
+                           int n_ctas, void* stream);
 
 #ifdef __cplusplus
 }

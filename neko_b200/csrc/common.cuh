@@ -114,6 +114,26 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
   dy = fmaf(x * 0.39894228040143267794f, e, x >= 0.0f ? 1.0f - h : h);
 }
 
+// ---- GELU, tanh form (HF "gelu_new", what pretrained GPT-2 checkpoints use: gato_policy.py:79-95 with --pretrained_lm) ----
+// 0.5 x (1 + tanh(u)) = x sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3);  d/dx = s + x s (1 - s) 2 u'
+__device__ __forceinline__ float gelu_tanh_sig(float x, float& x2) {
+  x2 = x * x;
+  const float u2 = x * fmaf(0.044715f * 1.5957691216057308f, x2, 1.5957691216057308f);   // 2u
+  return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * u2));
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  float x2;
+  return x * gelu_tanh_sig(x, x2);
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  float x2;
+  const float sg = gelu_tanh_sig(x, x2);
+  const float du2 = fmaf(3.0f * 0.044715f * 1.5957691216057308f, x2, 1.5957691216057308f);      // d(2u)/dx
+  return fmaf(x * sg * (1.0f - sg), du2, sg);
+}
+
+template <bool TANH> __device__ __forceinline__ float gelu_grad_sel(float x) { return TANH ? gelu_tanh_grad(x) : gelu_erf_grad(x); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -59,6 +60,7 @@ struct GemmParams {
   int n_fast;      // tile rasterisation: consecutive work units walk N first (else M first)
   int pair;        // 1: cta_group::2 CTA pairs (256 x BN tile per pair)
   int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
+  int tma_aux;     // RESID_F32 / DGELU: the auxiliary operand arrives as TMA boxes in the staging ring (prefetched, coalesced)
   int kb_per_split;
   DropCfg drop;    // RESID epilogues: C = aux + dropout(acc + bias)
 };
@@ -87,6 +89,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
   }
   const bool fast = (ncols == 32) && p.vec_ok;
   const bool c_f16 = (p.flags & NEKO_GEMM_C_F16) != 0, c2_f16 = (p.flags & NEKO_GEMM_C2_F16) != 0;
+  const bool gtanh = (p.flags & NEKO_GEMM_GELU_TANH) != 0;
   switch (p.epi) {
     case NEKO_EPI_BF16:
     case NEKO_EPI_GELU_BF16:
@@ -96,21 +99,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
         const bf16* a = reinterpret_cast<const bf16*>(p.aux) + row * p.ld_aux + col0;
         if (fast) {
           const uint4* a4 = reinterpret_cast<const uint4*>(a);
+          auto body = [&](auto tag) {
+            constexpr bool T = decltype(tag)::value;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 u = a4[i];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = a4[i];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 pre = unpack_bf16x2(w[j]);
-              f[8 * i + 2 * j] *= gelu_erf_grad(pre.x);
-              f[8 * i + 2 * j + 1] *= gelu_erf_grad(pre.y);
+              for (int j = 0; j < 4; ++j) {
+                const float2 pre = unpack_bf16x2(w[j]);
+                f[8 * i + 2 * j] *= gelu_grad_sel<T>(pre.x);
+                f[8 * i + 2 * j + 1] *= gelu_grad_sel<T>(pre.y);
+              }
             }
-          }
+          };
+          if (gtanh) body(std::true_type{}); else body(std::false_type{});
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < ncols) f[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+            if (i < ncols) f[i] *= gtanh ? gelu_tanh_grad(__bfloat162float(a[i])) : gelu_erf_grad(__bfloat162float(a[i]));
         }
       }
       if (fast) {
@@ -127,7 +134,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
       if (p.epi == NEKO_EPI_GELU_BF16) {
         uint16_t* c2 = reinterpret_cast<uint16_t*>(p.C2) + row * p.ldc2 + col0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        if (gtanh) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        }
         if (fast) {
           uint4* c4 = reinterpret_cast<uint4*>(c2);
 #pragma unroll
@@ -291,14 +304,20 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
     }
   }
   const bool c_f16 = (p.flags & NEKO_GEMM_C_F16) != 0, c2_f16 = (p.flags & NEKO_GEMM_C2_F16) != 0;
+  const bool gtanh = (p.flags & NEKO_GEMM_GELU_TANH) != 0;
   switch (p.epi) {
     case NEKO_EPI_BF16:
       stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
       break;
     case NEKO_EPI_GELU_BF16:
       stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      if (gtanh) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+      }
       stage_and_store(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
       if (p.C3) stage_and_store(s, mc3, f, 1, false, col0, row0);
       break;
@@ -307,21 +326,25 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
         const bf16* a = reinterpret_cast<const bf16*>(p.aux) + row * p.ld_aux + col0;
         if (fast) {
           const uint4* a4 = reinterpret_cast<const uint4*>(a);
+          auto body = [&](auto tag) {
+            constexpr bool T = decltype(tag)::value;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 u = a4[i];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = a4[i];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 pre = unpack_bf16x2(w[j]);
-              f[8 * i + 2 * j] *= gelu_erf_grad(pre.x);
-              f[8 * i + 2 * j + 1] *= gelu_erf_grad(pre.y);
+              for (int j = 0; j < 4; ++j) {
+                const float2 pre = unpack_bf16x2(w[j]);
+                f[8 * i + 2 * j] *= gelu_grad_sel<T>(pre.x);
+                f[8 * i + 2 * j + 1] *= gelu_grad_sel<T>(pre.y);
+              }
             }
-          }
+          };
+          if (gtanh) body(std::true_type{}); else body(std::false_type{});
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < ncols) f[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+            if (i < ncols) f[i] *= gtanh ? gelu_tanh_grad(__bfloat162float(a[i])) : gelu_erf_grad(__bfloat162float(a[i]));
         }
       }
       stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
@@ -363,6 +386,88 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
 }
 
 // ---------------------------------------------------------------------------------------------
+// Epilogue of one tile for the two epilogues that read an auxiliary operand (RESID_F32: C = aux + dropout(acc + bias), fp32;
+// DGELU: C = acc * gelu'(aux), 16-bit).  The aux box of a 32 x 32 chunk is brought into this warp's staging slot by TMA
+// (issued one chunk ahead, the first two before the accumulator is even complete), combined in place and stored from the
+// same slot: the aux read is asynchronous and coalesced instead of 32 row-strided 16-byte loads per warp instruction.
+// ---------------------------------------------------------------------------------------------
+template <bool F32>
+__device__ __forceinline__ void aux_issue(uint8_t* slot, const CUtensorMap* map_aux, uint32_t bar, int lane, int col0, int row0) {
+  if (lane == 0) {
+    mbar_expect_tx(bar, F32 ? 4096u : 2048u);
+    tma_load_2d(smem_u32(slot), map_aux, bar, col0, row0);
+  }
+}
+
+template <bool F32>
+__device__ __forceinline__ void aux_combine_store(const GemmParams& p, uint8_t* b, const CUtensorMap* mc, uint32_t (&v)[32], int lane,
+                                                  long long row, int row0, int col0) {
+  const int ncols = min(32, p.N - col0);
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  const int r = lane;
+  if (F32) {
+    if (p.bias) {
+      if (ncols == 32) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + i);
+          f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) f[i] += __ldg(p.bias + col0 + i);
+      }
+    }
+    if (p.drop.seed) {  // resid_dropout on the branch output, before the residual add
+      const uint32_t rk = drop_rowkey(drop_key(p.drop), (uint32_t)row);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float m0, m1;
+        drop_pair(rk, (uint32_t)((col0 >> 1) + i), p.drop.thr16, p.drop.scale, m0, m1);
+        f[2 * i] *= m0; f[2 * i + 1] *= m1;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4* q = reinterpret_cast<float4*>(b + r * 128 + ((c ^ (r & 7)) << 4));
+      const float4 a = *q;
+      *q = make_float4(f[4 * c] + a.x, f[4 * c + 1] + a.y, f[4 * c + 2] + a.z, f[4 * c + 3] + a.w);
+    }
+  } else {
+    const bool h = (p.flags & NEKO_GEMM_C_F16) != 0;
+    const bool gtanh = (p.flags & NEKO_GEMM_GELU_TANH) != 0;
+    auto body = [&](auto tag) {
+      constexpr bool T = decltype(tag)::value;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4* q = reinterpret_cast<uint4*>(b + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+        const uint4 u = *q;
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 pre = unpack_bf16x2(w[j]);
+          g[2 * j] = f[8 * c + 2 * j] * gelu_grad_sel<T>(pre.x);
+          g[2 * j + 1] = f[8 * c + 2 * j + 1] * gelu_grad_sel<T>(pre.y);
+        }
+        *q = make_uint4(pack_16x2(g[0], g[1], h), pack_16x2(g[2], g[3], h), pack_16x2(g[4], g[5], h), pack_16x2(g[6], g[7], h));
+      }
+    };
+    if (gtanh) body(std::true_type{}); else body(std::false_type{});
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(mc, smem_u32(b), col0, row0);
+    tma_store_commit();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
 // PAIR = true: the two CTAs of a cluster (one TPC) form a cta_group::2 pair that computes one 256 x BN tile.  Each CTA
@@ -373,7 +478,7 @@ template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
-                    const __grid_constant__ CUtensorMap map_c3, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap map_c3, const __grid_constant__ CUtensorMap map_aux, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -393,6 +498,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * stages + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  auto aux_bar = [&](int e, int slot) { return bar0 + 8u * (2 * stages + 5 + 2 * e + slot); };   // per epilogue warp, per staging slot
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -409,6 +515,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // pair: both CTAs' epilogues release the leader
+    }
+    for (int e = 0; e < GEMM_EPI_WARPS; ++e) {
+      mbar_init(aux_bar(e, 0), 1);
+      mbar_init(aux_bar(e, 1), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -536,23 +646,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     stg.wide = (p.epi == NEKO_EPI_F32 || p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16) ? 1 : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t aux_phase[2] = {0u, 0u};
+    const bool aux_f32 = (p.epi == NEKO_EPI_RESID_F32);
+    const int aux_slot_bytes = aux_f32 ? 4096 : 2048;
     for (long long u = u_first; u < units; u += u_step) {
       const long long t = u / p.splits;
       const bool split_first = (u - t * p.splits) == 0;
       const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * TM + (int)rank * BM;
       const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const long long row = (long long)m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tc_ld32(taddr + (uint32_t)(c * 32), v);
-        if (p.tma_store) epilogue_chunk_staged(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
-        else if (row < p.M) epilogue_chunk(p, v, row, col0);
+      if (p.tma_aux) {
+        // chunks of this warp: c = half * nch + cc.  The aux boxes of the first two are requested before the accumulator
+        // is complete (the main loop of this tile is still running), later ones one chunk ahead.
+        const int nch = BN / 64;
+        const int c_first = half * nch;
+        int n_live = 0;
+        for (int cc = 0; cc < nch; ++cc) n_live += (n0 + (c_first + cc) * 32 < p.N) ? 1 : 0;
+        const int row0 = m0 + q * 32;
+        if (lane == 0) tma_store_wait_read<0>();     // the previous tile's stores have read both slots
+        __syncwarp();
+        for (int cc = 0; cc < 2 && cc < n_live; ++cc) {
+          if (aux_f32) aux_issue<true>(stg.base + cc * aux_slot_bytes, &map_aux, aux_bar(e, cc), lane, n0 + (c_first + cc) * 32, row0);
+          else         aux_issue<false>(stg.base + cc * aux_slot_bytes, &map_aux, aux_bar(e, cc), lane, n0 + (c_first + cc) * 32, row0);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        for (int cc = 0; cc < n_live; ++cc) {
+          const int slot = cc & 1;
+          const int col0 = n0 + (c_first + cc) * 32;
+          uint32_t v[32];
+          tc_ld32(taddr + (uint32_t)((c_first + cc) * 32), v);
+          mbar_wait(aux_bar(e, slot), aux_phase[slot]);
+          aux_phase[slot] ^= 1u;
+          uint8_t* b = stg.base + slot * aux_slot_bytes;
+          if (aux_f32) aux_combine_store<true>(p, b, &map_c, v, lane, row, row0, col0);
+          else         aux_combine_store<false>(p, b, &map_c, v, lane, row, row0, col0);
+          if (cc + 2 < n_live) {     // refill this slot with the aux box of chunk cc + 2 once its store has read it out
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            if (aux_f32) aux_issue<true>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + 2) * 32, row0);
+            else         aux_issue<false>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + 2) * 32, row0);
+          }
+        }
+      } else {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int c = half * (BN / 64) + cc;
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tc_ld32(taddr + (uint32_t)(c * 32), v);
+          if (p.tma_store) epilogue_chunk_staged(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
+          else if (row < p.M) epilogue_chunk(p, v, row, col0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -741,7 +889,7 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   }
   const int bnl = p.pair ? p.BN / 2 : p.BN;  // B rows staged per CTA
   const int stage_bytes = BM * BK * 2 + bnl * BK * 2;
-  p.stages = (SMEM_BUDGET - 1024 - 256 - STAGING_BYTES) / stage_bytes;
+  p.stages = (SMEM_BUDGET - 1024 - 512 - STAGING_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   const bool out_bf16 = (epilogue == NEKO_EPI_BF16 || epilogue == NEKO_EPI_GELU_BF16 || epilogue == NEKO_EPI_DGELU_BF16);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -757,9 +905,20 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   const int c_esz = out_bf16 ? 2 : 4;
   p.tma_store = (tma_ok(C, ldc, c_esz) && tma_ok(C2, ldc2, 2) && tma_ok(C3, ldc3, 2)) ? 1 : 0;
   if (getenv("NEKO_GEMM_DIRECT_STORE")) p.tma_store = 0;
-  CUtensorMap ma, mb, mc, mc2, mc3;
-  memset(&mc, 0, sizeof(mc)); memset(&mc2, 0, sizeof(mc2)); memset(&mc3, 0, sizeof(mc3));
+  CUtensorMap ma, mb, mc, mc2, mc3, maux;
+  memset(&mc, 0, sizeof(mc)); memset(&mc2, 0, sizeof(mc2)); memset(&mc3, 0, sizeof(mc3)); memset(&maux, 0, sizeof(maux));
   int rc;
+  // the auxiliary operand of the residual / GELU' epilogues through TMA boxes (same staging slots as the output)
+  static const bool no_tma_aux = getenv("NEKO_GEMM_NO_TMA_AUX") != nullptr;
+  p.tma_aux = 0;
+  if (p.tma_store && !no_tma_aux && p.splits == 1 && (epilogue == NEKO_EPI_RESID_F32 || epilogue == NEKO_EPI_DGELU_BF16)) {
+    const int aesz = (epilogue == NEKO_EPI_RESID_F32) ? 4 : 2;
+    if (tma_ok(aux, ld_aux, aesz) && (bias == nullptr || al16(bias))) {
+      rc = make_map(&maux, aux, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ld_aux, 32, 32, aesz == 4 ? 2 : 3);
+      if (rc != NEKO_OK) return rc;
+      p.tma_aux = 1;
+    }
+  }
   if (p.tma_store) {
     const int ckind = out_bf16 ? ((flags & NEKO_GEMM_C_F16) ? 4 : 3) : 2;
     rc = make_map(&mc, C, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ldc, 32, 32, ckind);
@@ -780,7 +939,7 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   else         rc = make_map(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, BK, (flags & NEKO_GEMM_B_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
 
-  const size_t smem = (size_t)p.stages * stage_bytes + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)p.stages * stage_bytes + STAGING_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
@@ -805,11 +964,11 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, mc, mc2, mc3, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, mc, mc2, mc3, maux, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm pair)");
   } else {
     const int grid = (int)(units < sms ? units : sms);
-    cudaError_t e = launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), smem, as_stream(stream), ma, mb, mc, mc2, mc3, p);
+    cudaError_t e = launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm)");
   }
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");

@@ -45,6 +45,7 @@ class GradSynchronizer:
         self.average = average
         self.enabled = True
         self._pending: List[Tuple[int, int]] = []
+        self._tick = 0
         self._works = []
         self._cuda = arena.is_cuda
         self._stream = torch.cuda.Stream(device=arena.device) if self._cuda else None
@@ -57,6 +58,9 @@ class GradSynchronizer:
     def on_range_ready(self, lo: int, hi: int):
         if not self.enabled or self.world == 1:
             return
+        self._tick += 1
+        if self._p2p is not None and self._p2p.proto == "ce" and self.mode != "tail":
+            self._p2p.ce_drain(self._stream, self._tick)
         if self.mode == "tail":
             self._pending.append((lo, hi))
             return
@@ -70,12 +74,31 @@ class GradSynchronizer:
             self._flush()
 
     def _flush(self):
-        for lo, hi in self._pending:
-            for a, b in self._minus_skipped(lo, hi):
-                # split oversized ranges so that the first chunk can start while later ones are still queued
-                for s in range(a, b, self.bucket_elems):
-                    self._launch(s, min(b, s + self.bucket_elems))
+        pieces = [(a, b) for lo, hi in self._pending for a, b in self._minus_skipped(lo, hi)]
         self._pending = []
+        if self._cuda and self.backend == "p2p" and pieces and self._p2p_state().proto == "ce":
+            # copy-engine exchange: buckets are lists of ranges -- large pieces are cut at the bucket size, small neighbours
+            # (contiguous or not) share one exchange, i.e. one pair of flag rounds
+            group, total = [], 0
+            for a, b in pieces:
+                for s0 in range(a, b, self.bucket_elems):
+                    e0 = min(b, s0 + self.bucket_elems)
+                    if group and total + (e0 - s0) > self.bucket_elems:
+                        self._launch_group(group)
+                        group, total = [], 0
+                    group.append((s0, e0))
+                    total += e0 - s0
+            if group:
+                self._launch_group(group)
+            return
+        for a, b in pieces:
+            # split oversized ranges so that the first chunk can start while later ones are still queued
+            for s in range(a, b, self.bucket_elems):
+                self._launch(s, min(b, s + self.bucket_elems))
+
+    def _launch_group(self, group):
+        self.launched.extend(group)
+        self._p2p.ce_submit(list(group), 1.0 / self.world if self.average else 1.0, self._stream, self._tick)
 
     def _minus_skipped(self, lo: int, hi: int):
         out = [(lo, hi)]
@@ -96,15 +119,15 @@ class GradSynchronizer:
         view = self.arena[lo:hi]
         self.launched.append((lo, hi))
         op = dist.ReduceOp.SUM
-        if self._cuda:
+        if self._cuda and self.backend == "p2p" and self._p2p_state().proto == "ce":
+            self._p2p.ce_submit((lo, hi), 1.0 / self.world if self.average else 1.0, self._stream, self._tick)
+        elif self._cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.arena.device))
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
                 if self.backend == "p2p":
-                    if self._p2p is None:
-                        self._p2p = _P2PState(self.arena, self.group)
-                    self._p2p.all_reduce(lo, hi, 1.0 / self.world if self.average else 1.0)
+                    self._p2p_state().all_reduce(lo, hi, 1.0 / self.world if self.average else 1.0)
                 elif self.compress == "bf16":
                     if self._pack is None or self._pack.numel() < self.arena.numel():
                         self._pack = torch.empty(self.arena.numel(), dtype=torch.bfloat16, device=self.arena.device)
@@ -122,6 +145,20 @@ class GradSynchronizer:
             dist.all_reduce(view, op=op, group=self.group)
             if self.average:
                 view.mul_(1.0 / self.world)
+
+    def _p2p_state(self):
+        if self._p2p is None:
+            self._p2p = _P2PState(self.arena, self.group)
+        return self._p2p
+
+    def reduce_all(self):
+        """All-reduce every live range of the arena now, through the production path (bench.py's dp_grad_check, tests)."""
+        self.begin_step()
+        for a, b in self._minus_skipped(0, self.arena.numel()):
+            for s0 in range(a, b, self.bucket_elems):
+                self._launch(s0, min(b, s0 + self.bucket_elems))
+        self._pending = []
+        self.finish()
 
     # -- end of backward -----------------------------------------------------------------------------------
     def finish(self):
@@ -141,19 +178,27 @@ class GradSynchronizer:
                 for lo, hi in merged:
                     for a, b in self._minus_skipped(lo, hi):
                         self._launch(a, b)
+            elif self._cuda and self.backend == "p2p" and self._p2p_state().proto == "ce":
+                # everything still pending at the end of backward travels as ONE multi-range bucket: this exchange is exposed, and
+                # each separate one would pay its own two flag rounds and copy launches
+                self._flush()
             else:
                 self._flush()
         if self._cuda:
+            if self._p2p is not None and self._p2p.proto == "ce":
+                self._p2p.ce_flush(self._stream)
             torch.cuda.current_stream(self.arena.device).wait_stream(self._stream)
 
     def begin_step(self):
         self.launched = []
+        if self._p2p is not None:
+            self._p2p.begin_step()
 
     def finish_tail(self):
         """mode "tail": called by the policy after backward (eager or graph replay) -- reduce everything now."""
         if self.world == 1 or not self.enabled:
             return
-        self.launched = []
+        self.begin_step()
         self._pending = list(self._tail_ranges)
         self.finish()
 
@@ -180,8 +225,20 @@ class _P2PState:
         self.arena = arena
         dev = arena.device
         self.sig = torch.zeros(64, dtype=torch.int32, device=dev)          # [world] signal words (+ padding)
-        self.state = torch.zeros(2, dtype=torch.int32, device=dev)         # launch counter, CTA arrival counter
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)         # launch counter, CTA arrival counter, signal_wait counter
         self.n_ctas = int(__import__('os').environ.get('NEKO_P2P_CTAS', 0)) or int(self._lib.neko_sm_count())
+        # protocol: "ce" (default) copy engines move the data, one-warp flag kernels + a local reduction; "push" / "pull"
+        # SM-resident kernels (csrc/p2p_allreduce.cu explains why they lose next to the GEMMs)
+        self.proto = __import__('os').environ.get('NEKO_P2P_PROTO', 'ce')
+        assert self.proto in ("ce", "push", "pull")
+        self.push = self.proto != "pull"
+        # staging for the push protocol: `world` planes; plane r receives rank r's contributions to the slices this rank owns
+        self.plane = ((arena.numel() + self.world - 1) // self.world + 4 * 8192 + 63) // 64 * 64
+        self.stage = torch.empty(self.world * self.plane, dtype=torch.float32, device=dev) if self.push else None
+        self.stage_off = 0
+        self._ce_fifo = []
+        self._peer_streams = None
+        self.trace = None
         torch.cuda.synchronize(dev)
 
         def export(t):
@@ -190,7 +247,8 @@ class _P2PState:
             check(self._lib.neko_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)), "neko_ipc_export")
             return bytes(h), int(off.value)
 
-        mine = {"arena": export(arena), "sig": export(self.sig), "numel": arena.numel(), "pid": __import__("os").getpid()}
+        mine = {"arena": export(arena), "sig": export(self.sig), "numel": arena.numel(), "pid": __import__("os").getpid(),
+                "stage": export(self.stage) if self.push else None}
         every = [None] * self.world
         dist.all_gather_object(every, mine, group=group)
         if any(e["numel"] != arena.numel() for e in every):
@@ -204,21 +262,164 @@ class _P2PState:
             self._opened.append((out.value, pair[1]))
             return out.value
 
-        bufs, sigs = [], []
+        bufs, sigs, stages = [], [], []
         for r, e in enumerate(every):
             if r == self.rank:
                 bufs.append(arena.data_ptr())
                 sigs.append(self.sig.data_ptr())
+                stages.append(self.stage.data_ptr() if self.push else 0)
             else:
                 bufs.append(imp(e["arena"]))
                 sigs.append(imp(e["sig"]))
+                stages.append(imp(e["stage"]) if self.push else 0)
         self.bufs = (C.c_void_p * self.world)(*bufs)
         self.sigs = (C.c_void_p * self.world)(*sigs)
+        self.stages = (C.c_void_p * self.world)(*stages) if self.push else None
         dist.barrier(group=group)      # every signal buffer is zeroed and mapped before anybody launches
+
+    def begin_step(self):
+        self.stage_off = 0
+
+    def _mark(self, name, stream):
+        """tools/dp_trace.py: a timing event on `stream` (eager mode only)."""
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((name, e))
+
+    def _next_off(self, lo: int, hi: int) -> int:
+        per = ((hi - lo) // 4 + self.world - 1) // self.world * 4 + 16
+        if self.stage_off + per > self.plane:     # a caller that never calls begin_step: wrap (buckets this far apart never overlap in time)
+            self.stage_off = 0
+        off = self.stage_off
+        self.stage_off += per
+        return off
+
+    # ---- copy-engine protocol: a two-stage pipeline over the buckets of one backward --------------------------------
+    # bucket k ready  -> [comm stream]    DMA-push my copy of slice p into rank p's staging plane (one copy stream per peer, so the
+    #                    W-1 copies run on different engines at once), flag round
+    # >= 2 hook calls later (or finish) -> [COMPUTE stream] reduce slice r of bucket k: a wide, short kernel between two kernels of
+    #                    backward (a reduction kernel on the side stream would hold SMs the next persistent GEMM needs)
+    #                 -> [comm stream]    DMA-broadcast the reduced slice into every arena, flag round
+    # A bucket is a LIST of arena ranges exchanged under one pair of flag rounds (the small ranges at the end of backward --
+    # image stack, position tables, separator, the non-text rows of embed_token -- travel together with the last layer).
+    def _fan_out(self, comm, copies):
+        """copies: [(peer, dst_ptr, src_ptr, bytes)].  Runs them on the per-peer copy streams, forked from / joined into `comm`."""
+        C, lib, check = self._C, self._lib, self._check
+        if not copies:
+            return
+        if self.world == 2 or len({c[0] for c in copies}) == 1:
+            st = C.c_void_p(comm.cuda_stream)
+            for _p, dst, src, nb in copies:
+                check(lib.neko_memcpy_async(C.c_void_p(dst), C.c_void_p(src), C.c_longlong(nb), st), "neko_memcpy_async")
+            return
+        if self._peer_streams is None:
+            self._peer_streams = [torch.cuda.Stream(device=self.arena.device) for _ in range(self.world)]
+        fork = torch.cuda.Event()
+        fork.record(comm)
+        used = []
+        for p, dst, src, nb in copies:
+            ps = self._peer_streams[p]
+            if ps not in used:
+                ps.wait_event(fork)
+                used.append(ps)
+            check(lib.neko_memcpy_async(C.c_void_p(dst), C.c_void_p(src), C.c_longlong(nb), C.c_void_p(ps.cuda_stream)), "neko_memcpy_async")
+        for ps in used:
+            j = torch.cuda.Event()
+            j.record(ps)
+            comm.wait_event(j)
+
+    def _signal(self, comm):
+        C = self._C
+        self._check(self._lib.neko_p2p_signal_wait(self.sigs, C.c_void_p(self.state.data_ptr()), C.c_int(self.rank), C.c_int(self.world),
+                                                   C.c_void_p(comm.cuda_stream)), "neko_p2p_signal_wait")
+
+    def ce_submit(self, ranges, scale: float, comm, tick: int = 0):
+        if isinstance(ranges, tuple):
+            ranges = [ranges]
+        cur = torch.cuda.current_stream(self.arena.device)
+        W, r = self.world, self.rank
+        offs = [self._next_off(lo, hi) for lo, hi in ranges]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        tag = "+".join(f"[{lo >> 20}M..{hi >> 20}M)" for lo, hi in ranges)
+        self._mark("ready   " + tag, cur)
+        mine = self.arena.data_ptr()
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev)
+            self._mark("  push> " + tag, comm)
+            copies = []
+            for (lo, hi), off in zip(ranges, offs):
+                for pp in range(1, W):
+                    p = (r + pp) % W
+                    a, ln = self._span(lo, hi, p)
+                    if ln:
+                        copies.append((p, self.stages[p] + 4 * (r * self.plane + off), mine + 4 * (lo + a), 4 * ln))
+            self._fan_out(comm, copies)
+            self._mark("  push< " + tag, comm)
+            self._signal(comm)
+            self._mark("  land  " + tag, comm)
+            landed = torch.cuda.Event()
+            landed.record(comm)
+        self._ce_fifo.append((list(ranges), scale, offs, landed, tick, tag))
+
+    def _span(self, lo: int, hi: int, p: int):
+        n = hi - lo
+        per = ((n // 4 + self.world - 1) // self.world) * 4
+        a = min(n, p * per)
+        return a, min(n, (p + 1) * per) - a
+
+    def ce_drain(self, comm, tick=None, min_age: int = 2):
+        """Reduce + broadcast the buckets pushed at least `min_age` hook calls ago (all of them when tick is None).  The delay is
+        static (it has to be: the schedule is captured into a CUDA graph): by then the pushes have landed and the compute
+        stream does not wait."""
+        cur = torch.cuda.current_stream(self.arena.device)
+        while self._ce_fifo and (tick is None or tick - self._ce_fifo[0][4] >= min_age):
+            self._ce_reduce(self._ce_fifo.pop(0), cur, comm)
+
+    def _ce_reduce(self, pend, cur, comm):
+        ranges, scale, offs, landed, _tick, tag = pend
+        C, lib, check, W, r = self._C, self._lib, self._check, self.world, self.rank
+        mine = self.arena.data_ptr()
+        self._mark("red-enq " + tag, cur)
+        cur.wait_event(landed)
+        self._mark("red>    " + tag, cur)
+        for (lo, hi), off in zip(ranges, offs):
+            a, ln = self._span(lo, hi, r)
+            if ln:
+                check(lib.neko_reduce_planes_f32(C.c_void_p(mine + 4 * (lo + a)), C.c_void_p(self.stage.data_ptr() + 4 * off),
+                                                 C.c_longlong(self.plane), C.c_int(W), C.c_int(r), C.c_longlong(ln), C.c_float(scale),
+                                                 C.c_void_p(cur.cuda_stream)), "neko_reduce_planes_f32")
+        reduced = torch.cuda.Event()
+        reduced.record(cur)
+        self._mark("red<    " + tag, cur)
+        with torch.cuda.stream(comm):
+            comm.wait_event(reduced)
+            self._mark("  bcast>" + tag, comm)
+            copies = []
+            for lo, hi in ranges:
+                a, ln = self._span(lo, hi, r)
+                if ln:
+                    for pp in range(1, W):
+                        p = (r + pp) % W
+                        copies.append((p, self.bufs[p] + 4 * (lo + a), mine + 4 * (lo + a), 4 * ln))
+            self._fan_out(comm, copies)
+            self._mark("  bcast<" + tag, comm)
+            self._signal(comm)
+            self._mark("  done  " + tag, comm)
+
+    def ce_flush(self, comm):
+        self.ce_drain(comm, None)
 
     def all_reduce(self, lo: int, hi: int, scale: float):
         C = self._C
-        self._check(self._lib.neko_p2p_allreduce_f32(self.bufs, self.sigs, C.c_void_p(self.state.data_ptr()), C.c_int(self.rank),
+        if self.proto == "ce":      # standalone use (tools): the same pipeline, drained at once on one stream
+            cur = torch.cuda.current_stream(self.arena.device)
+            self.ce_submit((lo, hi), scale, cur)
+            return self.ce_flush(cur)
+        off = self._next_off(lo, hi)
+        self._check(self._lib.neko_p2p_allreduce_f32(self.bufs, self.sigs, self.stages, C.c_longlong(self.plane), C.c_longlong(off),
+                                                     C.c_void_p(self.state.data_ptr()), C.c_int(self.rank),
                                                      C.c_int(self.world), C.c_longlong(lo), C.c_longlong(hi),
                                                      C.c_float(scale), C.c_int(self.n_ctas),
                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "neko_p2p_allreduce_f32")

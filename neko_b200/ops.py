@@ -16,7 +16,7 @@ from ._lib import (EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F
 
 
 _16BIT = (torch.bfloat16, torch.float16)
-GEMM_A_F16, GEMM_B_F16, GEMM_C_F16, GEMM_C2_F16 = 1, 2, 4, 8
+GEMM_A_F16, GEMM_B_F16, GEMM_C_F16, GEMM_C2_F16, GEMM_GELU_TANH = 1, 2, 4, 8, 16
 GEMM_TIMING = None  # list collecting (start_event, end_event, flops) per launch when set by bench.py
 
 
@@ -37,7 +37,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, out3: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, accumulate: bool = False,
          M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
-         out_dtype: torch.dtype = torch.bfloat16, drop: Optional[Dropout] = None):
+         out_dtype: torch.dtype = torch.bfloat16, drop: Optional[Dropout] = None, gelu_tanh: bool = False):
     """C[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: 16-bit [M,K] (a_mn=False) or [K,M] (a_mn=True); b: same format, [N,K] or [K,N]; rows may be strided
@@ -60,6 +60,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     flags = (GEMM_A_F16 | GEMM_B_F16) if a.dtype == torch.float16 else 0
     flags |= GEMM_C_F16 if out.dtype == torch.float16 else 0
     flags |= GEMM_C2_F16 if (out2 is not None and out2.dtype == torch.float16) else 0
+    flags |= GEMM_GELU_TANH if gelu_tanh else 0   # GELU / GELU' epilogues: tanh form ("gelu_new")
     gd = GemmDesc(M=M, N=N, K=K, a_mn=int(a_mn), b_mn=int(b_mn), epilogue=epilogue, accumulate=int(accumulate), flags=flags,
                   A=a.data_ptr(), lda=a.stride(0), B=b.data_ptr(), ldb=b.stride(0), C=out.data_ptr(), ldc=out.stride(0),
                   C2=_ptr(out2), ldc2=out2.stride(0) if out2 is not None else 0,

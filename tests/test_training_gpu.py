@@ -105,7 +105,8 @@ def test_trainer_steps_match_torch_adamw_on_oracle_gradients(lean, images_at):
     assert len(used) > 10
     for a, b in zip(losses, rlosses):
         assert abs(a - b) <= 2e-3 * abs(b), (losses, rlosses)
-    assert losses[-1] < losses[0]
+    if not images_at:       # same kind of batch every step: the loss must go down
+        assert losses[-1] < losses[0]
     # parameters after 4 AdamW steps: updates are O(lr) per step whatever the gradient scale, so compare in units of lr
     sd = m.state_dict()
     worst = 0.0
