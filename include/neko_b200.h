@@ -299,10 +299,10 @@ int neko_ipc_import(const unsigned char* handle /* 64 bytes */, long long offset
 int neko_ipc_close(void* dev_ptr, long long offset);
 /* Copy-engine flavour of the same all-reduce (what neko_b200/dp.py runs by default): NVLink traffic is moved by
  * neko_memcpy_async between peer-mapped buffers (DMA engines, no SM), neko_p2p_signal_wait is the one-warp cross-rank
- * barrier between the steps (signal words 32.. of the signal buffers, launch counter in state[2]) and
+ * barrier between the steps (per channel c: signal words 32 + 8c .. of the 64-word signal buffers, launch counter in state[2 + c] of the 8-word state) and
  * neko_reduce_planes_f32 sums the staged contributions: dst[i] = scale * sum_q (q == self ? dst[i] : stage[q*plane+i]). */
 int neko_memcpy_async(void* dst, const void* src, long long bytes, void* stream);
-int neko_p2p_signal_wait(void* const* host_sigs, unsigned* state, int rank, int world, void* stream);
+int neko_p2p_signal_wait(void* const* host_sigs, unsigned* state, int rank, int world, int channel /* 0..3 */, void* stream);
 int neko_reduce_planes_f32(float* dst, const float* stage, long long plane, int n_planes, int self, long long n, float scale, void* stream);
 /* host_stage (nullable): HOST array of `world` device pointers to every rank's staging buffer (world planes of stage_plane
  * floats each).  When given, the exchange runs push style -- contributions are WRITTEN into the owner's staging planes

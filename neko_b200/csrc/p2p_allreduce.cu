@@ -217,16 +217,18 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_push_kernel(const P
 // the only kernels are a one-warp flag exchange and the local reduction of the staged planes.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) p2p_signal_wait_kernel(const P2PArgs a) {
-  // state[2]: launches of THIS kernel so far; signal words 32.. of every rank's signal buffer belong to this protocol
-  const unsigned want = *reinterpret_cast<volatile unsigned*>(a.state + 2) + 1u;
+  // channel c = a.flags (0..3): independent barrier sequences, so that exchanges running on different streams do not have
+  // to agree on one global order.  state[2 + c]: launches on this channel so far; signal words 32 + 8 c .. belong to it
+  const int ch = a.flags;
+  const unsigned want = *reinterpret_cast<volatile unsigned*>(a.state + 2 + ch) + 1u;
   __threadfence_system();
   if ((int)threadIdx.x < a.world) {
-    st_release_sys(a.sig[threadIdx.x] + 32 + a.rank, want);
-    const unsigned* mine = a.sig[a.rank] + 32 + threadIdx.x;
-    while ((int)(ld_acquire_sys(mine) - want) < 0) __nanosleep(200);
+    st_release_sys(a.sig[threadIdx.x] + 32 + 8 * ch + a.rank, want);
+    const unsigned* mine = a.sig[a.rank] + 32 + 8 * ch + threadIdx.x;
+    while ((int)(ld_acquire_sys(mine) - want) < 0) __nanosleep(100);
   }
   __syncwarp();
-  if (threadIdx.x == 0) a.state[2] = want;
+  if (threadIdx.x == 0) a.state[2 + ch] = want;
 }
 
 // dst[i] = scale * sum over planes q in rank order (plane `self` is dst itself, the others are the staged contributions)
@@ -282,16 +284,17 @@ int neko_memcpy_async(void* dst, const void* src, long long bytes, void* stream)
   return check_cuda(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, as_stream(stream)), "cudaMemcpyAsync");
 }
 
-int neko_p2p_signal_wait(void* const* host_sigs, unsigned* state, int rank, int world, void* stream) {
+int neko_p2p_signal_wait(void* const* host_sigs, unsigned* state, int rank, int world, int channel, void* stream) {
   using namespace neko;
-  NEKO_REQUIRE(host_sigs && state && world >= 2 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "p2p_signal_wait: bad arguments");
+  NEKO_REQUIRE(host_sigs && state && world >= 2 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world && channel >= 0 && channel < 4,
+               "p2p_signal_wait: bad arguments");
   P2PArgs a;
   memset(&a, 0, sizeof(a));
   for (int p = 0; p < world; ++p) {
     NEKO_REQUIRE(host_sigs[p], "p2p_signal_wait: null signal pointer %d", p);
     a.sig[p] = static_cast<unsigned*>(host_sigs[p]);
   }
-  a.state = state; a.rank = rank; a.world = world;
+  a.state = state; a.rank = rank; a.world = world; a.flags = channel;
   static bool carve = false;
   if (!carve) {
     cudaError_t e = cudaFuncSetAttribute(p2p_signal_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

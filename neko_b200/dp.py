@@ -42,6 +42,9 @@ class GradSynchronizer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = max(1, bucket_bytes // arena.element_size())
+        # ranges that complete within the last `tail_elems` live elements of the arena are exchanged at once instead of
+        # waiting for a full bucket: at the end of backward nothing is left to hide a big exchange behind
+        self.tail_elems = (48 << 20) // arena.element_size()
         self.average = average
         self.enabled = True
         self._pending: List[Tuple[int, int]] = []
@@ -70,7 +73,8 @@ class GradSynchronizer:
         else:
             self._flush()
             self._pending.append((lo, hi))
-        if self._pending[-1][1] - self._pending[-1][0] >= self.bucket_elems:
+        if self._pending[-1][1] - self._pending[-1][0] >= self.bucket_elems or self._live_after(self._pending[-1][1]) <= self.tail_elems:
+            # full bucket -- or close to the end of backward, where whatever waits for company is exposed later
             self._flush()
 
     def _flush(self):
@@ -99,6 +103,10 @@ class GradSynchronizer:
     def _launch_group(self, group):
         self.launched.extend(group)
         self._p2p.ce_submit(list(group), 1.0 / self.world if self.average else 1.0, self._stream, self._tick)
+
+    def _live_after(self, pos: int) -> int:
+        """Arena elements after `pos` that still take part in the exchange (the arena is laid out in completion order)."""
+        return sum(b - a for a, b in self._minus_skipped(pos, self.arena.numel()))
 
     def _minus_skipped(self, lo: int, hi: int):
         out = [(lo, hi)]
@@ -225,7 +233,7 @@ class _P2PState:
         self.arena = arena
         dev = arena.device
         self.sig = torch.zeros(64, dtype=torch.int32, device=dev)          # [world] signal words (+ padding)
-        self.state = torch.zeros(4, dtype=torch.int32, device=dev)         # launch counter, CTA arrival counter, signal_wait counter
+        self.state = torch.zeros(8, dtype=torch.int32, device=dev)         # launch counter, CTA arrival counter, signal_wait counters per channel
         self.n_ctas = int(__import__('os').environ.get('NEKO_P2P_CTAS', 0)) or int(self._lib.neko_sm_count())
         # protocol: "ce" (default) copy engines move the data, one-warp flag kernels + a local reduction; "push" / "pull"
         # SM-resident kernels (csrc/p2p_allreduce.cu explains why they lose next to the GEMMs)
@@ -238,6 +246,9 @@ class _P2PState:
         self.stage_off = 0
         self._ce_fifo = []
         self._peer_streams = None
+        self._comm = None
+        self._n_submitted = 0
+        self.two_channels = __import__('os').environ.get('NEKO_P2P_CHANNELS', '2') != '1'
         self.trace = None
         torch.cuda.synchronize(dev)
 
@@ -279,6 +290,7 @@ class _P2PState:
 
     def begin_step(self):
         self.stage_off = 0
+        self._n_submitted = 0
 
     def _mark(self, name, stream):
         """tools/dp_trace.py: a timing event on `stream` (eager mode only)."""
@@ -303,7 +315,7 @@ class _P2PState:
     #                 -> [comm stream]    DMA-broadcast the reduced slice into every arena, flag round
     # A bucket is a LIST of arena ranges exchanged under one pair of flag rounds (the small ranges at the end of backward --
     # image stack, position tables, separator, the non-text rows of embed_token -- travel together with the last layer).
-    def _fan_out(self, comm, copies):
+    def _fan_out(self, comm, copies, ch: int = 0):
         """copies: [(peer, dst_ptr, src_ptr, bytes)].  Runs them on the per-peer copy streams, forked from / joined into `comm`."""
         C, lib, check = self._C, self._lib, self._check
         if not copies:
@@ -314,12 +326,12 @@ class _P2PState:
                 check(lib.neko_memcpy_async(C.c_void_p(dst), C.c_void_p(src), C.c_longlong(nb), st), "neko_memcpy_async")
             return
         if self._peer_streams is None:
-            self._peer_streams = [torch.cuda.Stream(device=self.arena.device) for _ in range(self.world)]
+            self._peer_streams = [[torch.cuda.Stream(device=self.arena.device) for _ in range(self.world)] for _c in range(2)]
         fork = torch.cuda.Event()
         fork.record(comm)
         used = []
         for p, dst, src, nb in copies:
-            ps = self._peer_streams[p]
+            ps = self._peer_streams[ch][p]
             if ps not in used:
                 ps.wait_event(fork)
                 used.append(ps)
@@ -329,16 +341,26 @@ class _P2PState:
             j.record(ps)
             comm.wait_event(j)
 
-    def _signal(self, comm):
+    def _signal(self, comm, ch: int = 0):
         C = self._C
         self._check(self._lib.neko_p2p_signal_wait(self.sigs, C.c_void_p(self.state.data_ptr()), C.c_int(self.rank), C.c_int(self.world),
-                                                   C.c_void_p(comm.cuda_stream)), "neko_p2p_signal_wait")
+                                                   C.c_int(ch), C.c_void_p(comm.cuda_stream)), "neko_p2p_signal_wait")
+
+    def _channel(self, comm):
+        """Buckets alternate between two exchange streams (own flag channel each): the push of bucket k+1 does not queue
+        behind the broadcast of bucket k."""
+        if self._comm is None or self._comm[0] is not comm:
+            self._comm = [comm, torch.cuda.Stream(device=self.arena.device)]
+        ch = self._n_submitted % 2 if self.two_channels else 0
+        self._n_submitted += 1
+        return ch, self._comm[ch]
 
     def ce_submit(self, ranges, scale: float, comm, tick: int = 0):
         if isinstance(ranges, tuple):
             ranges = [ranges]
         cur = torch.cuda.current_stream(self.arena.device)
         W, r = self.world, self.rank
+        ch, comm = self._channel(comm)
         offs = [self._next_off(lo, hi) for lo, hi in ranges]
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -355,13 +377,13 @@ class _P2PState:
                     a, ln = self._span(lo, hi, p)
                     if ln:
                         copies.append((p, self.stages[p] + 4 * (r * self.plane + off), mine + 4 * (lo + a), 4 * ln))
-            self._fan_out(comm, copies)
+            self._fan_out(comm, copies, ch)
             self._mark("  push< " + tag, comm)
-            self._signal(comm)
+            self._signal(comm, ch)
             self._mark("  land  " + tag, comm)
             landed = torch.cuda.Event()
             landed.record(comm)
-        self._ce_fifo.append((list(ranges), scale, offs, landed, tick, tag))
+        self._ce_fifo.append((list(ranges), scale, offs, landed, tick, tag, ch))
 
     def _span(self, lo: int, hi: int, p: int):
         n = hi - lo
@@ -375,10 +397,11 @@ class _P2PState:
         stream does not wait."""
         cur = torch.cuda.current_stream(self.arena.device)
         while self._ce_fifo and (tick is None or tick - self._ce_fifo[0][4] >= min_age):
-            self._ce_reduce(self._ce_fifo.pop(0), cur, comm)
+            self._ce_reduce(self._ce_fifo.pop(0), cur)
 
-    def _ce_reduce(self, pend, cur, comm):
-        ranges, scale, offs, landed, _tick, tag = pend
+    def _ce_reduce(self, pend, cur):
+        ranges, scale, offs, landed, _tick, tag, ch = pend
+        comm = self._comm[ch]
         C, lib, check, W, r = self._C, self._lib, self._check, self.world, self.rank
         mine = self.arena.data_ptr()
         self._mark("red-enq " + tag, cur)
@@ -403,13 +426,16 @@ class _P2PState:
                     for pp in range(1, W):
                         p = (r + pp) % W
                         copies.append((p, self.bufs[p] + 4 * (lo + a), mine + 4 * (lo + a), 4 * ln))
-            self._fan_out(comm, copies)
+            self._fan_out(comm, copies, ch)
             self._mark("  bcast<" + tag, comm)
-            self._signal(comm)
+            self._signal(comm, ch)
             self._mark("  done  " + tag, comm)
 
     def ce_flush(self, comm):
+        """Drain the pipeline; afterwards `comm` (the synchroniser's stream) is ordered after both exchange streams."""
         self.ce_drain(comm, None)
+        if self._comm is not None and self._comm[1] is not comm:
+            comm.wait_stream(self._comm[1])
 
     def all_reduce(self, lo: int, hi: int, scale: float):
         C = self._C

@@ -82,15 +82,18 @@ print("dp ok", rank)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("backend", ["p2p", "nccl"])
+@pytest.mark.parametrize("backend", ["p2p", "p2p-push", "p2p-pull", "nccl"])
 def test_dp_gradients_match_mean_of_ranks(tmp_path, backend):
-    """backend p2p: the own peer-memory all-reduce kernel (csrc/p2p_allreduce.cu, the default); nccl: torch.distributed."""
+    """backend p2p: the own all-reduce over peer-mapped arenas (csrc/p2p_allreduce.cu) -- copy-engine pipeline (the default),
+    or the SM-resident push / pull kernels; nccl: torch.distributed."""
+    proto = {"p2p": "ce", "p2p-push": "push", "p2p-pull": "pull"}.get(backend, "ce")
+    backend = backend.split("-")[0]
     script = tmp_path / "dp_worker.py"
     script.write_text(_WORKER)
-    port = 29700 + (os.getpid() % 1000) + (7 if backend == "p2p" else 0)
+    port = 29700 + (os.getpid() % 1000) + {"ce": 7, "push": 13, "pull": 19}[proto] * (backend == "p2p")
     procs = []
     for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NEKO_ROOT=ROOT, NEKO_DP_BACKEND=backend)
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NEKO_ROOT=ROOT, NEKO_DP_BACKEND=backend, NEKO_P2P_PROTO=proto)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     for p in procs:
         out, _ = p.communicate(timeout=150)

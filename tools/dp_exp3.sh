@@ -1,5 +1,3 @@
 N=${1:-2}; CFG=${2:-cfg2}
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --config $CFG --steps 30 --warmup 5 --no-cpu-baseline --only 2>&1 | python tools/bench_line.py "$1"; }
-NEKO_DP_BACKEND=p2p NEKO_DP_BUCKET_MB=64 run p2p_ce_b64
-NEKO_DP_BACKEND=p2p NEKO_DP_BUCKET_MB=32 run p2p_ce_b32
-NEKO_DP_BACKEND=nccl run nccl_overlap
+NEKO_DP_BACKEND=p2p run p2p_ce_default
