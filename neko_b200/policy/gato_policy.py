@@ -121,6 +121,30 @@ class _OfflineTextTokenizer:
     decode = encode
 
 
+def _load_pretrained_gpt2(path: str):
+    """--pretrained_lm (gato_policy.py:79-95): configuration + tensors of a HF GPT-2 checkpoint directory (config.json +
+    model.safetensors / pytorch_model.bin).  A hub name is resolved from the local HF cache only (there may be no network)."""
+    import json
+    import os
+    if not os.path.isdir(path):
+        try:
+            from huggingface_hub import snapshot_download
+            path = snapshot_download(path, local_files_only=True)
+        except Exception as e:  # noqa: BLE001
+            raise FileNotFoundError(f"--pretrained_lm={path!r}: not a local checkpoint directory and not in the local Hugging Face cache "
+                                    f"({type(e).__name__}); download it first or pass the directory") from e
+    with open(os.path.join(path, "config.json")) as f:
+        cfg = json.load(f)
+    st = os.path.join(path, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        sd = load_file(st)
+    else:
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    sd = {(n[len("transformer."):] if n.startswith("transformer.") else n): t for n, t in sd.items()}
+    return cfg, sd
+
+
 def _load_text_tokenizer(name: str):
     try:
         from transformers import AutoTokenizer
@@ -207,8 +231,14 @@ class GatoPolicy(nn.Module):
         self.device = dev
         with torch.cuda.device(dev):
             _lib.require_device()
+        lm_cfg = lm_sd = None
         if pretrained_lm is not None:
-            raise NotImplementedError("--pretrained_lm needs the HF hub (SURVEY.md section 8(f).4)")
+            # gato_policy.py:79-95: the decoder's shape, activation and weights come from the GPT-2 checkpoint; embed_dim /
+            # layers / heads / activation_fn arguments are overridden, exactly as in the reference
+            print("loading pretrained GPT2 weights")
+            lm_cfg, lm_sd = _load_pretrained_gpt2(pretrained_lm)
+            embed_dim, heads, layers = int(lm_cfg["n_embd"]), int(lm_cfg["n_head"]), int(lm_cfg["n_layer"])
+            activation_fn = lm_cfg.get("activation_function", "gelu_new")
         assert embed_dim % heads == 0
         if (embed_dim // heads) not in (16, 32, 64, 128):
             raise NotImplementedError(f"head dim {embed_dim // heads} not supported (16/32/64/128)")
@@ -223,20 +253,31 @@ class GatoPolicy(nn.Module):
         self.token_ends = {"text": self.text_tokens - 1, "continuous": self.text_tokens + self.continuous_tokens - 1,
                            "discrete": self.text_tokens + self.continuous_tokens + self.discrete_tokens - 1}
         gate = False
-        if activation_fn == "geglu":
+        if activation_fn == "geglu" and lm_cfg is None:
             gate = True
             activation_fn = "gelu"
-        if activation_fn != "gelu":
-            raise NotImplementedError(f"activation_fn={activation_fn!r}: only 'gelu' (erf) and 'geglu' exist in the reference CLI")
+        if activation_fn not in ("gelu", "gelu_new"):
+            raise NotImplementedError(f"activation_fn={activation_fn!r}: 'gelu' (erf), 'geglu' (reference CLI) and 'gelu_new' (tanh form of "
+                                      "pretrained GPT-2 checkpoints) are implemented")
+        self._gelu_tanh = activation_fn == "gelu_new"      # GELU / GELU' GEMM epilogues: tanh form
         self.heads = heads
         self.layers = layers
         self.dropout = dropout
         self.mu, self.M = mu, M
         self.patch_size = patch_size
-        config = _GPT2Config(vocab_size=1, n_embd=embed_dim, n_head=heads, n_layer=layers, resid_pdrop=dropout,
-                             attn_pdrop=dropout, embd_pdrop=0.1, n_positions=context_len, n_ctx=context_len,
-                             n_inner=embed_dim * 4, activation_function=activation_fn, flash=flash, gate=gate,
-                             layer_norm_epsilon=1e-5)
+        if lm_cfg is None:
+            config = _GPT2Config(vocab_size=1, n_embd=embed_dim, n_head=heads, n_layer=layers, resid_pdrop=dropout,
+                                 attn_pdrop=dropout, embd_pdrop=0.1, n_positions=context_len, n_ctx=context_len,
+                                 n_inner=embed_dim * 4, activation_function=activation_fn, flash=flash, gate=gate,
+                                 layer_norm_epsilon=1e-5)
+        else:
+            if lm_cfg.get("n_inner") not in (None, 4 * embed_dim):
+                raise NotImplementedError("pretrained GPT-2 with n_inner != 4 * n_embd")
+            n_ctx = int(lm_cfg.get("n_ctx", lm_cfg.get("n_positions", 1024)))
+            config = _GPT2Config(vocab_size=int(lm_cfg["vocab_size"]), n_embd=embed_dim, n_head=heads, n_layer=layers, resid_pdrop=dropout,
+                                 attn_pdrop=dropout, embd_pdrop=float(lm_cfg.get("embd_pdrop", 0.1)), n_positions=int(lm_cfg.get("n_positions", n_ctx)),
+                                 n_ctx=n_ctx, n_inner=embed_dim * 4, activation_function=activation_fn, flash=flash, gate=False,
+                                 layer_norm_epsilon=float(lm_cfg.get("layer_norm_epsilon", 1e-5)))
         with torch.device(dev):
             self.transformer = GPT2Model(config)
             self.embed_token = _EmbeddingParams(self.vocab_size, embed_dim)
@@ -253,6 +294,17 @@ class GatoPolicy(nn.Module):
                                                   use_pos_encoding=use_patch_pos_encoding)
             self.use_pos_encoding = use_pos_encoding
             self.pos_embed_observation = _EmbeddingParams(context_len, embed_dim)
+        if lm_sd is not None:
+            own = dict(self.transformer.named_parameters())
+            assert tuple(lm_sd["wte.weight"].shape) == (self.text_tokens, embed_dim), "pretrained token/expected mimsatch"
+            missing = [n for n in own if n not in lm_sd]
+            if missing:
+                raise KeyError(f"--pretrained_lm checkpoint lacks {missing[:4]} ...")
+            with torch.no_grad():
+                for n, p in own.items():          # wpe (no absolute positions here, trajectory_gpt2.py:540) and attn.bias are not taken
+                    p.copy_(lm_sd[n].to(dev, torch.float32).reshape(p.shape))
+                # expand the embedding dictionary up to vocab_size: the text rows start from the LM's table (gato_policy.py:91-93)
+                self.embed_token.weight[:self.text_tokens] = self.transformer.wte.weight
         ref = weakref.ref(self)
         object.__setattr__(self.transformer, "_owner", ref)
         object.__setattr__(self.image_embedding, "_owner", ref)
@@ -1008,7 +1060,7 @@ class GatoPolicy(nn.Module):
             fgate = None
             if not gate:
                 ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
-                         out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias)
+                         out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias, gelu_tanh=self._gelu_tanh)
             else:   # geglu: h = gelu(c_fc(x)) * gated_layer(x)   (trajectory_gpt2.py:267-276; nn.Linear weight is [out, in])
                 gelu_o = self._buf("fgelu", (N, 4 * d), fdt)
                 ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=gelu_o,
@@ -1315,7 +1367,7 @@ class GatoPolicy(nn.Module):
             dpre = self._buf("dfpre", (N, 4 * d), torch.bfloat16)
             dln = self._buf("dln", (N, d), torch.bfloat16)
             if fgate is None:
-                ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre)
+                ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_DGELU_BF16, out=dpre, aux=fpre, gelu_tanh=self._gelu_tanh)
             else:   # geglu: dh -> (d_gate, d_pre); the gate Linear gets its own wgrad / bias grad / dgrad
                 dh4 = self._buf("dfh", (N, 4 * d), torch.bfloat16)
                 ops.gemm(dxb, Wb(pre + "mlp.c_proj.weight"), epilogue=ops.EPI_BF16, out=dh4)

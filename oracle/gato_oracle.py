@@ -58,8 +58,9 @@ class GatoConfig:
     use_pos_encoding: bool = True
     use_patch_pos_encoding: bool = True
     pad_seq: bool = False
-    activation_fn: str = "gelu"  # 'geglu' adds the gate, trajectory_gpt2.py:267-276
+    activation_fn: str = "gelu"  # 'geglu' adds the gate, trajectory_gpt2.py:267-276; 'gelu_new' = the tanh form of a pretrained GPT-2 config
     layer_norm_eps: float = 1e-5
+    wte_rows: int = 1  # transformer.wte is a dead [1, d] table (vocab_size=1, gato_policy.py:102) unless --pretrained_lm brings GPT-2's own
 
     @property
     def vocab_size(self) -> int:  # gato_policy.py:63
@@ -413,7 +414,9 @@ def decoder(x: torch.Tensor, token_masks: torch.Tensor, w: Dict[str, torch.Tenso
             o = o * drop[("resid_attn", i)]
         x = o + x
         m = F.layer_norm(x, (d,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], cfg.layer_norm_eps)
-        hmid = gelu_erf(torch.addmm(w[p + "mlp.c_fc.bias"], m.reshape(-1, d), w[p + "mlp.c_fc.weight"]))
+        hpre = torch.addmm(w[p + "mlp.c_fc.bias"], m.reshape(-1, d), w[p + "mlp.c_fc.weight"])
+        # ACT2FN[config.activation_function] (trajectory_gpt2.py:266): 'gelu' = erf form, 'gelu_new' = tanh form (pretrained GPT-2)
+        hmid = F.gelu(hpre, approximate="tanh") if cfg.activation_fn == "gelu_new" else gelu_erf(hpre)
         if cfg.activation_fn == "geglu":
             hmid = hmid * F.linear(m.reshape(-1, d), w[p + "mlp.gated_layer.weight"], w[p + "mlp.gated_layer.bias"])
         m = torch.addmm(w[p + "mlp.c_proj.bias"], hmid, w[p + "mlp.c_proj.weight"]).reshape(B, S, d)
@@ -507,7 +510,7 @@ def predict_control(w: Dict[str, torch.Tensor], inp: dict, cfg: GatoConfig, acti
 def weight_shapes(cfg: GatoConfig) -> Dict[str, tuple]:
     """state_dict parameter names/shapes of the reference policy."""
     d, C, p = cfg.embed_dim, cfg.resid_mid_channels, cfg.patch_size
-    s: Dict[str, tuple] = {"separator_token": (d,), "transformer.wte.weight": (1, d)}
+    s: Dict[str, tuple] = {"separator_token": (d,), "transformer.wte.weight": (cfg.wte_rows, d)}
     for i in range(cfg.layers):
         q = f"transformer.h.{i}."
         s.update({

@@ -141,7 +141,41 @@ def install_shims() -> None:
     # (6) HF-4.30.2 behaviour of init_weights / get_head_mask for a model without tied weights
     tg.GPT2PreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
     tg.GPT2Model.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+
+    # (7) --pretrained_lm (gato_policy.py:79-95): HF 5's from_pretrained needs post_init bookkeeping the reference's class does
+    # not have, and with shim (6) its init pass re-initialises the weights it has just loaded.  Restore the HF-4.30.2
+    # outcome: construct through HF, then put the checkpoint's tensors back (wpe / attn.bias are not part of the class).
+    tg.GPT2PreTrainedModel.all_tied_weights_keys = {}
+    _orig_from_pretrained = tg.GPT2Model.from_pretrained.__func__
+
+    def _from_pretrained(cls, path, *a, **k):
+        m = _orig_from_pretrained(cls, path, *a, **k)
+        sd = load_gpt2_checkpoint(path)
+        own = m.state_dict()
+        m.load_state_dict({n: t for n, t in sd.items() if n in own and not n.endswith((".attn.bias", ".attn.masked_bias"))}, strict=False)
+        # HF 5 builds the module on the meta device: the causal-mask buffers Attention.__init__ computes
+        # (trajectory_gpt2.py:127-130) come back uninitialised.  Recompute them as __init__ does.
+        import torch
+        for blk in m.h:
+            n_ctx = blk.attn.bias.shape[-1]
+            blk.attn.bias = torch.tril(torch.ones((n_ctx, n_ctx), dtype=torch.uint8)).view(1, 1, n_ctx, n_ctx)
+            blk.attn.masked_bias = torch.tensor(-1e4)
+        return m
+
+    tg.GPT2Model.from_pretrained = classmethod(_from_pretrained)
     _installed = True
+
+
+def load_gpt2_checkpoint(path: str):
+    """Tensors of a local HF GPT-2 checkpoint directory (model.safetensors or pytorch_model.bin), 'transformer.' prefix stripped."""
+    import torch
+    st = os.path.join(path, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        sd = load_file(st)
+    else:
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    return {(n[len("transformer."):] if n.startswith("transformer.") else n): t for n, t in sd.items()}
 
 
 def load_reference_policy_class():

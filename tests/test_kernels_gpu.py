@@ -131,6 +131,41 @@ def test_gemm_epilogues(ops):
     assert (out.float() - acc * p.grad).abs().max().item() < 0.1
 
 
+def test_gemm_gelu_tanh_epilogues(ops):
+    """gelu_new (tanh form, pretrained GPT-2: gato_policy.py:79-95) in the GELU / GELU' epilogues.  The two GELU forms differ by
+    < 5e-4, below one 16-bit ulp, so the check is statistical: with B = I the pre-activation is exact, rounding errors average
+    out over 64k elements and the mean signed error tells the forms apart."""
+    M, N = 512, 128
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(M, N, generator=g) * 0.8 + 1.8).cuda().to(torch.bfloat16)      # where tanh - erf (2.4e-4) and its derivative (6.6e-4) have one sign
+    eye = torch.eye(N, device="cuda", dtype=torch.bfloat16)
+    F = torch.nn.functional
+    xf = x.float()
+    gap = (F.gelu(xf, approximate="tanh") - F.gelu(xf)).mean().item()
+    assert abs(gap) > 1e-4
+    for tanh in (True, False):
+        pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        act = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        ops.gemm(x, eye, epilogue=ops.EPI_GELU_BF16, out=pre, out2=act, gelu_tanh=tanh)
+        assert torch.equal(pre, x)
+        ref = F.gelu(xf, approximate="tanh") if tanh else F.gelu(xf)
+        other = F.gelu(xf) if tanh else F.gelu(xf, approximate="tanh")
+        assert (act.float() - ref).abs().max().item() < 2.5e-3
+        assert abs((act.float() - ref).mean().item()) < 0.3 * abs(gap) < abs((act.float() - other).mean().item())
+    # derivative: acc = 1 (ones @ I / N trick: A = ones, B = I), aux = x
+    ones = torch.ones(M, N, device="cuda", dtype=torch.bfloat16)
+    for tanh in (True, False):
+        p = xf.clone().requires_grad_(True)
+        (F.gelu(p, approximate="tanh") if tanh else F.gelu(p)).sum().backward()
+        q = xf.clone().requires_grad_(True)
+        (F.gelu(q) if tanh else F.gelu(q, approximate="tanh")).sum().backward()
+        dgap = (p.grad - q.grad).mean().item()
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        ops.gemm(ones, eye, epilogue=ops.EPI_DGELU_BF16, aux=x, out=out, gelu_tanh=tanh)
+        assert (out.float() - p.grad).abs().max().item() < 2e-3
+        assert abs((out.float() - p.grad).mean().item()) < 0.3 * abs(dgap) < abs((out.float() - q.grad).mean().item())
+
+
 @pytest.mark.parametrize("a_dt,b_dt", [(torch.float16, torch.float16)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (False, True)])
 def test_gemm_fp16_operands(ops, a_dt, b_dt, a_mn, b_mn):

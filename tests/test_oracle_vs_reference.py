@@ -146,3 +146,35 @@ def test_inference_loops_match_reference():
         d_ref = m.predict_control(dict(images=img.clone(), discrete_actions=dact.clone()), task, deterministic=True)
     d_or = O.predict_control(w, dict(images=img.clone(), discrete_actions=dact.clone()), cfg, action_tokens=1, discrete_n=4)
     assert int(d_ref) == int(d_or)
+
+
+def test_pretrained_lm_path_matches_oracle(tmp_path):
+    """--pretrained_lm (gato_policy.py:79-95) through the shims: GPT2Model.from_pretrained of a local GPT-2 checkpoint, gelu_new,
+    wte copied into the text rows of embed_token -- the oracle with activation 'gelu_new' reproduces it, the erf form does not."""
+    import transformers
+    cfg = transformers.GPT2Config(vocab_size=300, n_embd=64, n_layer=2, n_head=4, n_positions=128, n_ctx=128)
+    torch.manual_seed(5)
+    hf = transformers.GPT2Model(cfg)
+    with torch.no_grad():
+        for p in hf.parameters():
+            p.mul_(4.0)
+    hf.save_pretrained(str(tmp_path))
+    ref_shim.set_text_vocab(300)
+    G = ref_shim.load_reference_policy_class()
+    g = G(device="cpu", embed_dim=8, layers=1, heads=1, dropout=0.0, resid_mid_channels=128, context_len=128, pretrained_lm=str(tmp_path))
+    ref_shim.set_text_vocab(50257)
+    g.transformer.drop.p = 0.0
+    g.eval()
+    raw = ref_shim.load_gpt2_checkpoint(str(tmp_path))
+    assert torch.equal(g.transformer.h[1].attn.c_attn.bias.detach(), raw["h.1.attn.c_attn.bias"])
+    assert torch.equal(g.embed_token.weight[:300].detach(), raw["wte.weight"]) and g.embed_dim == 64
+    sd = {k: v.detach().clone() for k, v in g.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+    batch = [{"text": list(range(1, 40))}, {"continuous_obs": torch.randn(5, 3), "continuous_actions": torch.rand(5, 2)}]
+    logits, loss = g(batch, compute_loss=True)
+    errs = {}
+    for act in ("gelu_new", "gelu"):
+        oc = O.GatoConfig(embed_dim=64, layers=2, heads=4, context_len=128, text_tokens=300, activation_fn=act, wte_rows=300)
+        assert set(sd) == set(O.weight_shapes(oc))
+        out = O.forward(sd, batch, oc, compute_loss=True)
+        errs[act] = (out.logits - logits.detach())[out.token_masks.bool()].abs().max().item()
+    assert errs["gelu_new"] < 2e-5 and errs["gelu"] > 1e-3, errs

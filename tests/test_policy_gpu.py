@@ -286,6 +286,65 @@ def test_init_distributions_match_reference():
             assert abs(float(t.min()) - lo_r) <= 0.05 * (hi_r - lo_r) and abs(float(t.max()) - hi_r) <= 0.05 * (hi_r - lo_r), n
 
 
+def _tiny_gpt2_checkpoint(tmp_path, vocab=300, d=64, layers=2, heads=2, n_ctx=128, scale=2.0):
+    """A local HF GPT-2 checkpoint directory (config.json + model.safetensors) with weights large enough that the erf and
+    tanh GELU forms differ visibly."""
+    import transformers
+    cfg = transformers.GPT2Config(vocab_size=vocab, n_embd=d, n_layer=layers, n_head=heads, n_positions=n_ctx, n_ctx=n_ctx)
+    torch.manual_seed(21)
+    m = transformers.GPT2Model(cfg)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(scale)
+    m.save_pretrained(str(tmp_path))
+    return str(tmp_path)
+
+
+def test_pretrained_lm_matches_oracle(tmp_path):
+    """--pretrained_lm (gato_policy.py:79-95): decoder shape / weights / gelu_new from a GPT-2 checkpoint directory, the text
+    rows of embed_token start from its wte, wpe is dropped.  Forward + backward against the oracle run with
+    activation 'gelu_new' (pinned to the reference's own pretrained path in tests/test_oracle_vs_reference.py)."""
+    from neko_b200.policy import GatoPolicy
+    from safetensors.torch import load_file
+    ckpt = _tiny_gpt2_checkpoint(tmp_path)
+    torch.manual_seed(3)
+    m = GatoPolicy(device="cuda", embed_dim=8, layers=1, heads=1, dropout=0.0, resid_mid_channels=128, context_len=96,
+                   pretrained_lm=ckpt, text_tokenizer=_Tok(300))     # embed_dim / layers / heads are overridden by the checkpoint
+    assert (m.embed_dim, m.layers, m.heads) == (64, 2, 2) and m._gelu_tanh
+    m.transformer.drop.p = 0.0
+    m.eval()
+    raw = load_file(os.path.join(ckpt, "model.safetensors"))
+    sd = m.state_dict()
+    assert tuple(sd["transformer.wte.weight"].shape) == (300, 64) and not any("wpe" in k for k in sd)
+    assert torch.equal(sd["transformer.h.1.mlp.c_fc.weight"].cpu(), raw["h.1.mlp.c_fc.weight"])
+    assert torch.equal(sd["embed_token.weight"][:300].cpu(), raw["wte.weight"])
+    cfg = O.GatoConfig(embed_dim=64, layers=2, heads=2, context_len=96, text_tokens=300, activation_fn="gelu_new", wte_rows=300)
+    w = {k: v.detach().cpu().clone() for k, v in sd.items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+    assert set(w) == set(O.weight_shapes(cfg))
+    batch = [dict(text=list(range(5, 60))), dict(continuous_obs=torch.randn(6, 4) * 2, continuous_actions=torch.rand(6, 2) * 2 - 1),
+             dict(images=torch.randint(0, 256, (1, 3, 32, 32), dtype=torch.uint8), text=torch.arange(7, 19))]
+    logits, loss = m(batch, compute_loss=True)
+    loss.backward()
+    for t in w.values():
+        t.requires_grad_(True)
+    ref = O.forward(w, batch, cfg, compute_loss=True)
+    ref.loss.backward()
+    valid = ref.token_masks.bool()
+    lerr = (logits.detach().cpu() - ref.logits.detach())[valid].abs().max().item()
+    # the checkpoint's weights are scaled up 4x here: the absolute logit gate scales with the logits' spread (0.58 at normal init)
+    spread = max(1.0, float(ref.logits.detach()[valid].std()) / 0.58)
+    print('pretrained: logits err', lerr, 'spread factor', spread)
+    assert lerr <= LOGIT_TOL * spread and abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (lerr, spread, loss.item(), ref.loss.item())
+    # (that the tanh form is really what the epilogues compute is checked at kernel level: test_gemm_gelu_tanh_epilogues)
+    rep = _grad_report(m, w)
+    bad = {n: v for n, v in rep.items() if v[2] > 1e-6 and v[0] < 0.99}
+    assert not bad, bad
+    assert min(v[0] for n, v in rep.items() if n.endswith("c_fc.weight") or n.endswith("mlp.c_proj.weight")) > 0.999
+    with pytest.raises(FileNotFoundError):
+        GatoPolicy(device="cuda", embed_dim=64, layers=1, heads=2, dropout=0.0, resid_mid_channels=128, pretrained_lm="no-such-model",
+                   text_tokenizer=_Tok(300))
+
+
 def test_kwargs_path_matches_inputs_path():
     cfg = O.GatoConfig(**SMALL_CASES["mixed"]["cfg"])
     w = O.make_weights(cfg, seed=3)
