@@ -45,6 +45,11 @@ class GradSynchronizer:
         # ranges that complete within the last `tail_elems` live elements of the arena are exchanged at once instead of
         # waiting for a full bucket: at the end of backward nothing is left to hide a big exchange behind
         self.tail_elems = (48 << 20) // arena.element_size()
+        # ... and what completes within the last `nccl_tail_elems` goes through NCCL (p2p backend, copy-engine protocol)
+        self.nccl_tail = __import__("os").environ.get("NEKO_DP_NCCL_TAIL", "0") == "1"   # measured: no gain over the copy-engine tail (profiles/r02_dp_experiments.txt)
+        self.nccl_tail_elems = (16 << 20) // arena.element_size()
+        self._nccl_stream = None
+        self._nccl_used = False
         self.average = average
         self.enabled = True
         self._pending: List[Tuple[int, int]] = []
@@ -81,6 +86,13 @@ class GradSynchronizer:
         pieces = [(a, b) for lo, hi in self._pending for a, b in self._minus_skipped(lo, hi)]
         self._pending = []
         if self._cuda and self.backend == "p2p" and pieces and self._p2p_state().proto == "ce":
+            # the very end of backward (the last layer's matrices, the embedding tables): no GEMM is left to disturb and
+            # nothing left to hide a multi-step exchange behind -- NCCL's one-kernel all-reduce is the shortest path there
+            if self.nccl_tail:
+                late = [(a, b) for a, b in pieces if self._live_after(b) <= self.nccl_tail_elems]
+                pieces = [pc for pc in pieces if pc not in late]
+                for a, b in late:
+                    self._launch_nccl(a, b)
             # copy-engine exchange: buckets are lists of ranges -- large pieces are cut at the bucket size, small neighbours
             # (contiguous or not) share one exchange, i.e. one pair of flag rounds
             group, total = [], 0
@@ -99,6 +111,21 @@ class GradSynchronizer:
             # split oversized ranges so that the first chunk can start while later ones are still queued
             for s in range(a, b, self.bucket_elems):
                 self._launch(s, min(b, s + self.bucket_elems))
+
+    def _launch_nccl(self, lo: int, hi: int):
+        self.launched.append((lo, hi))
+        if self._nccl_stream is None:
+            self._nccl_stream = torch.cuda.Stream(device=self.arena.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.arena.device))
+        with torch.cuda.stream(self._nccl_stream):
+            self._nccl_stream.wait_event(ev)
+            view = self.arena[lo:hi]
+            if self.average:
+                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        self._nccl_used = True
 
     def _launch_group(self, group):
         self.launched.extend(group)
@@ -195,6 +222,9 @@ class GradSynchronizer:
         if self._cuda:
             if self._p2p is not None and self._p2p.proto == "ce":
                 self._p2p.ce_flush(self._stream)
+            if self._nccl_used:
+                torch.cuda.current_stream(self.arena.device).wait_stream(self._nccl_stream)
+                self._nccl_used = False
             torch.cuda.current_stream(self.arena.device).wait_stream(self._stream)
 
     def begin_step(self):

@@ -20,6 +20,9 @@ for d in data[:1]:
             if h.endswith(k):
                 print(f"  {k:70s} {d[i]:>16s} {units[i]}")
                 break
+    for i, h in enumerate(hdr):      # tensor-pipe utilisation, whatever this ncu version calls it
+        if "pipe_tensor" in h and ("pct" in h or "cycles_active" in h):
+            print(f"  {h:70s} {d[i]:>16s} {units[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
