@@ -211,6 +211,11 @@ int neko_masked_ce_fwd(const float* logits, int64_t ld_logits, int V, const int3
 int neko_masked_ce_fused(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
                          const int64_t* tokens, float* row_lse, float* row_loss, float* loss,
                          uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream);
+/* The same pass over fp16 logits (the head GEMM of the training path that returns no logits writes them in 16 bits): V*2
+ * bytes read per row instead of V*4; statistics in fp32.  Same return convention. */
+int neko_masked_ce_fused_f16(const uint16_t* logits_f16, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
+                             const int64_t* tokens, float* row_lse, float* row_loss, float* loss, uint16_t* dlogits,
+                             int64_t ld_dlogits, int flags, void* stream);
 int neko_ce_scale_grad(uint16_t* dlogits, int64_t n, const float* gscale, void* stream);
 int neko_masked_ce_bwd(const float* logits, int64_t ld_logits, int V, const int32_t* rows, int n_rows,
                        const int64_t* tokens, const float* row_lse, const float* gscale,

@@ -6,6 +6,8 @@
 // (no sync); one CTA streams one selected logits row: online max / sum-exp in fp32, loss_i = lse - z[tgt].
 // Backward writes (softmax - onehot) * g / n_rows as bf16 straight into the dlogits operand of the head
 // dgrad / wgrad GEMMs.  HBM-bound: V*4 bytes read per selected row (+ V*2 written in backward).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace neko {
@@ -214,6 +216,90 @@ __global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same fused pass for 16-bit (fp16) logits: the training path that does not hand logits back to the caller
+// (materialize_logits = False, what the trainer runs: trainer.py:178 discards them) lets the head GEMM write fp16, so the
+// row costs V*2 bytes to write, V*2 to read here and V*2 to write as the gradient operand -- 6V instead of the 10V of the fp32
+// route (4V written by the GEMM, 4V read, 2V written).  Statistics are fp32; the fp16 rounding of a logit (<= 2^-11 relative)
+// moves the loss by ~1e-5 relative and the softmax by less than the bf16 rounding of the gradient itself.  The row buffer holds
+// the logits only (105 KB): pass 3 recomputes exp(z - lse) instead of keeping fp32 exponentials.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void h8_to_f(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(CEF_THREADS, 1) ce_fused_f16_kernel(const __half* __restrict__ logits, long long ld, int V,
+                                                                      const int32_t* __restrict__ rows, int n_rows,
+                                                                      const int64_t* __restrict__ tokens, float* __restrict__ row_lse,
+                                                                      float* __restrict__ row_loss, bf16* __restrict__ dlogits, long long ldd,
+                                                                      int flags) {
+  extern __shared__ __align__(16) uint4 cef_row_h[];   // [V rounded up to 8] halves
+  __shared__ float red[CEF_THREADS / 32];
+  const int nv = V >> 3;                                // full 8-element (16-byte) slots
+  const float inv_n = 1.0f / (float)n_rows;
+  __half* row_h = reinterpret_cast<__half*>(cef_row_h);
+  auto row_src = [&](int r) { return logits + ((flags & NEKO_CE_LOGITS_COMPACT) ? (long long)r : (long long)rows[r]) * ld; };
+  if (blockIdx.x < n_rows) {
+    const uint4* z8 = reinterpret_cast<const uint4*>(row_src(blockIdx.x));
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) cef_cp_async16(cef_row_h + i, z8 + i);
+    cef_cp_async_commit();
+  }
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const long long pos = rows[r];
+    const __half* z = row_src(r);
+    bf16* dz = dlogits + ((flags & NEKO_CE_DLOGITS_COMPACT) ? (long long)r : pos) * ldd;
+    const bool has_next = r + (int)gridDim.x < n_rows;
+    const uint4* zn8 = reinterpret_cast<const uint4*>(has_next ? row_src(r + (int)gridDim.x) : z);
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CEF_THREADS) row_h[i] = z[i];
+    cef_cp_async_wait_all();
+    float f[8];
+    // pass 1: maximum
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      h8_to_f(cef_row_h[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    }
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CEF_THREADS) mx = fmaxf(mx, __half2float(row_h[i]));
+    mx = cef_block_reduce(mx, true, red);
+    // pass 2: sum of exp(z - max)
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      h8_to_f(cef_row_h[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += __expf(f[j] - mx);
+    }
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CEF_THREADS) sum += __expf(__half2float(row_h[i]) - mx);
+    sum = cef_block_reduce(sum, false, red);
+    const int tgt = (int)tokens[pos + 1];
+    const float lse = mx + logf(sum);
+    if (threadIdx.x == 0) {
+      row_lse[r] = lse;
+      row_loss[r] = (tgt >= 0 && tgt < V) ? lse - __half2float(z[tgt]) : 0.f;
+    }
+    // pass 3: (softmax - onehot) / n_rows as bf16; each consumed slot starts loading the next row
+    uint4* d8 = reinterpret_cast<uint4*>(dz);
+    for (int i = threadIdx.x; i < nv; i += CEF_THREADS) {
+      h8_to_f(cef_row_h[i], f);
+      const int c = i << 3;
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = __expf(f[j] - lse) * inv_n - (c + j == tgt ? inv_n : 0.f);
+      d8[i] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+      if (has_next) cef_cp_async16(cef_row_h + i, zn8 + i);   // after the slot has been consumed (same thread, same slot)
+    }
+    cef_cp_async_commit();
+    __syncthreads();   // the scalar tail below reads row_h entries other threads wrote at the top of this iteration
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CEF_THREADS)
+      dz[i] = __float2bfloat16_rn(__expf(__half2float(row_h[i]) - lse) * inv_n - (i == tgt ? inv_n : 0.f));
+    if (flags & NEKO_CE_ZERO_PAD)
+      for (long long i = V + threadIdx.x; i < ldd; i += CEF_THREADS) dz[i] = __float2bfloat16_rn(0.f);
+    __syncthreads();   // ... and the next iteration overwrites them
+  }
+}
+
 // dlogits *= g unless g == 1 (bf16 [n_rows, ld], all columns)
 __global__ void __launch_bounds__(256) ce_scale_kernel(bf16* __restrict__ d, long long n8, const float* __restrict__ gscale) {
   const float g = __ldg(gscale);
@@ -274,6 +360,29 @@ int neko_masked_ce_fused(const float* logits, int64_t ld_logits, int V, const in
   ce_fused_kernel<<<grid, CEF_THREADS, smem, as_stream(stream)>>>(logits, ld_logits, V, rows, n_rows, tokens, row_lse, row_loss,
                                                                   reinterpret_cast<bf16*>(dlogits), ld_dlogits, flags);
   NEKO_LAUNCH_CHECK("ce_fused_kernel");
+  ce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_rows, loss);
+  NEKO_LAUNCH_CHECK("ce_mean_kernel");
+  return NEKO_OK;
+}
+
+int neko_masked_ce_fused_f16(const uint16_t* logits_f16, int64_t ld_logits, int V, const int32_t* rows, int n_rows, const int64_t* tokens,
+                             float* row_lse, float* row_loss, float* loss, uint16_t* dlogits, int64_t ld_dlogits, int flags, void* stream) {
+  using namespace neko;
+  NEKO_REQUIRE(logits_f16 && rows && tokens && row_lse && row_loss && loss && dlogits, "masked_ce_fused_f16: null pointer");
+  NEKO_REQUIRE(V > 0 && n_rows > 0 && ld_logits >= V && ld_dlogits >= V, "masked_ce_fused_f16: bad sizes");
+  const size_t smem = ((size_t)V + 7) / 8 * 16;
+  if (smem > 220 * 1024 || (ld_logits & 7) || (ld_dlogits & 7) || (reinterpret_cast<uintptr_t>(logits_f16) & 15) || (reinterpret_cast<uintptr_t>(dlogits) & 15))
+    return 1;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(ce_fused_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ce_fused_f16)");
+    attr = smem;
+  }
+  const int grid = n_rows < sm_count() ? n_rows : sm_count();
+  ce_fused_f16_kernel<<<grid, CEF_THREADS, smem, as_stream(stream)>>>(reinterpret_cast<const __half*>(logits_f16), ld_logits, V, rows, n_rows, tokens,
+                                                                      row_lse, row_loss, reinterpret_cast<bf16*>(dlogits), ld_dlogits, flags);
+  NEKO_LAUNCH_CHECK("ce_fused_f16_kernel");
   ce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_rows, loss);
   NEKO_LAUNCH_CHECK("ce_mean_kernel");
   return NEKO_OK;

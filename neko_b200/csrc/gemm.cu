@@ -940,14 +940,14 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   if (rc != NEKO_OK) return rc;
 
   const size_t smem = (size_t)p.stages * stage_bytes + STAGING_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm pair)");
-    attr_set = true;
-  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
   const long long units = mb_ * ((N + p.BN - 1) / p.BN) * p.splits;
   if (p.pair) {
     const int pairs = sms / 2;

@@ -201,8 +201,10 @@ def masked_ce_fused(logits: torch.Tensor, V: int, rows: torch.Tensor, tokens: to
     row_lse = torch.empty(n, device=logits.device, dtype=torch.float32)
     row_loss = torch.empty(n, device=logits.device, dtype=torch.float32)
     loss = torch.empty((), device=logits.device, dtype=torch.float32)
-    rc = load().neko_masked_ce_fused(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens), _p(row_lse),
-                                     _p(row_loss), _p(loss), _p(dlogits), C.c_int64(dlogits.stride(-2)), C.c_int(flags), stream_ptr())
+    fn = load().neko_masked_ce_fused_f16 if logits.dtype == torch.float16 else load().neko_masked_ce_fused
+    assert logits.dtype in (torch.float16, torch.float32)
+    rc = fn(_p(logits), C.c_int64(logits.stride(-2)), C.c_int(V), _p(rows), C.c_int(n), _p(tokens), _p(row_lse),
+            _p(row_loss), _p(loss), _p(dlogits), C.c_int64(dlogits.stride(-2)), C.c_int(flags), stream_ptr())
     if rc == 1:
         return None
     check(rc, "neko_masked_ce_fused")

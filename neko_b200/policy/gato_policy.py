@@ -313,6 +313,7 @@ class GatoPolicy(nn.Module):
         # are exactly zero); 'dense' runs them over every position like the reference's autograd.  Identical gradients.
         self.head_mode = "rows"
         self.materialize_logits = True  # False: head evaluated on loss rows only, forward returns logits=None
+        self.lean_logits_f16 = True     # ... and, when gradients are wanted, those logits live in fp16 between head GEMM and fused CE
         # 16-bit format of the FORWARD operands (activations fed to GEMMs, weight copy).  fp16 has 3 more mantissa
         # bits than bf16 at the same tensor-core rate and brings logits max-abs error from 2.1e-2 to ~6e-3 at
         # d=768/L=6 (DESIGN.md "precision"); gradients stay bf16 for range, the residual stream stays fp32.
@@ -1086,11 +1087,17 @@ class GatoPolicy(nn.Module):
             st.acts, st.x_last, st.hf, st.mf, st.rf = acts, x, hf_b, mf, rf
         return hf
 
-    def _head(self, hf: torch.Tensor, n_rows: int) -> torch.Tensor:
+    def _head(self, hf: torch.Tensor, n_rows: int, f16: bool = False) -> torch.Tensor:
         """predict_token (gato_policy.py:172): fp32 logits [n_rows, Vp] (columns >= V are exact zeros).  Freshly
-        allocated (torch's caching allocator) because the caller keeps the tensor."""
-        logits = torch.empty(n_rows, self._Vp, dtype=torch.float32, device=self.device)
-        ops.gemm(hf, self._wview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_F32, out=logits, N=self._Vp)
+        allocated (torch's caching allocator) because the caller keeps the tensor.  ``f16``: the training path that never
+        returns logits (materialize_logits = False) keeps them in fp16 in a workspace buffer -- they only feed the fused
+        cross entropy, which reads V*2 instead of V*4 bytes per row (csrc/ce.cu: ce_fused_f16_kernel)."""
+        if f16:
+            logits = self._buf("logits_rows_f16", (n_rows, self._Vp), torch.float16)
+            ops.gemm(hf, self._wview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_BF16, out=logits, N=self._Vp)
+        else:
+            logits = torch.empty(n_rows, self._Vp, dtype=torch.float32, device=self.device)
+            ops.gemm(hf, self._wview("predict_token.weight", rows=self._Vp), epilogue=ops.EPI_F32, out=logits, N=self._Vp)
         self.launches += 1
         return logits
 
@@ -1125,7 +1132,7 @@ class GatoPolicy(nn.Module):
         p = st.plan
         return (p.B, p.seq_len, p.width, p.descs.tobytes(), tuple((g.height, g.width, g.is_u8, g.n_frames) for g in p.image_groups),
                 len(p.precomputed_patch), st.compute_loss, st.need_grad, self.training, self.materialize_logits, self.head_mode,
-                self.fwd_dtype, st.row_bins is not None, self._dropout_ps())
+                self.fwd_dtype, st.row_bins is not None, self._dropout_ps(), self.lean_logits_f16)
 
     def _engine_forward(self, st: _State):
         if not self.use_cuda_graphs:
@@ -1206,9 +1213,16 @@ class GatoPolicy(nn.Module):
             if st.compute_loss and n_rows:
                 hc = self._buf("hf_rows", (n_rows, d), self.fwd_dtype)
                 ops.gather_rows(hf, st.loss_rows, d, hc)
-                full = self._head(hc, n_rows)
+                # with gradients wanted, the logits of the loss rows exist only between the head GEMM and the fused cross
+                # entropy: 16 bits are enough there (loss statistics stay fp32)
+                f16 = keep and self.lean_logits_f16 and hc.dtype == torch.float16 and (self._Vp * 2) <= 220 * 1024
+                full = self._head(hc, n_rows, f16=f16)
                 st.logits_full, st.hf_rows = full, hc
                 loss = self._ce_forward(st, full, V, n_rows, keep, ops.CE_LOGITS_COMPACT)
+                if f16 and not st.ce_fused:     # not applicable after all (alignment): take the fp32 route
+                    full = self._head(hc, n_rows)
+                    st.logits_full = full
+                    loss = self._ce_forward(st, full, V, n_rows, keep, ops.CE_LOGITS_COMPACT)
                 self.launches += 1
         return logits, loss
 
@@ -1224,6 +1238,8 @@ class GatoPolicy(nn.Module):
                 self.launches += 2
                 loss, st.row_lse = out
                 return loss
+        if full.dtype != torch.float32:
+            return None                     # 16-bit logits exist for the fused kernel only: the caller falls back to fp32
         loss, st.row_lse, _ = ops.masked_ce_fwd(full, V, st.loss_rows, st.tokens, flags=flags)
         self.launches += 2
         return loss

@@ -189,15 +189,19 @@ def test_head_modes_and_accumulation_agree():
     w = O.make_weights(cfg, seed=3)
     batch = small_batch("mixed", cfg.text_tokens)
     grads = {}
-    for mode in ("dense", "rows", "lean"):
+    for mode in ("dense", "rows", "lean", "lean32"):
         m = make_policy(cfg, w)
         m.head_mode = "rows" if mode != "dense" else "dense"
-        m.materialize_logits = mode != "lean"
+        m.materialize_logits = not mode.startswith("lean")
+        m.lean_logits_f16 = mode == "lean"      # default: the loss rows' logits live in fp16 between head GEMM and fused CE
         _, loss = m(batch, compute_loss=True)
         loss.backward()
         grads[mode] = ({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, loss.item())
-    for mode in ("rows", "lean"):
-        assert abs(grads[mode][1] - grads["dense"][1]) < 1e-5
+        if mode == "lean":
+            assert m._ws["logits_rows_f16"].dtype == torch.float16 and m._graphs == {}
+    for mode in ("rows", "lean", "lean32"):
+        # fp16 logits move the loss by ~1e-5 relative (gate: 1e-3); the fp32 routes agree to rounding
+        assert abs(grads[mode][1] - grads["dense"][1]) < (3e-4 if mode == "lean" else 1e-5), (mode, grads[mode][1], grads["dense"][1])
         for n, gd in grads["dense"][0].items():
             gr = grads[mode][0][n]
             assert (gd - gr).norm().item() <= 2e-2 * gd.norm().item() + 1e-7, (mode, n)
