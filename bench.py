@@ -308,6 +308,8 @@ def build_model(cfg_name, args, dev):
     model.transformer.drop.p = 0.0
     model.head_mode = args.head
     model.materialize_logits = not args.lean
+    if "NEKO_MLP_PROJ_BF16" in os.environ:      # experiment switch: forward mlp down-projection on bf16 operands
+        model.mlp_proj_bf16 = os.environ["NEKO_MLP_PROJ_BF16"] == "1"
     model.lean_logits_f16 = os.environ.get("NEKO_LEAN_F32") != "1"     # experiment switch: --lean with fp32 logits of the loss rows
     model.use_cuda_graphs = not args.no_graphs
     model.train()

@@ -32,11 +32,12 @@ namespace neko {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+// epilogue warps per CTA (template parameter EW): 8 = two per TMEM lane quarter, each owning half of the tile's columns (168
+// registers per thread), or 16 = four per quarter, a quarter of the columns each (<= 112 registers): twice the warps to hide the
+// tcgen05.ld -> math -> staging -> TMA-store chain of the epilogue-heavy launches behind
+constexpr int GEMM_EPI_WARPS_MAX = 16;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int STAGING_PER_WARP = 8192;  // ring of 2 fp32 boxes (32 rows x 128 B) or 4 16-bit boxes (32 rows x 64 B)
-constexpr int STAGING_BYTES = GEMM_EPI_WARPS * STAGING_PER_WARP;
+constexpr int STAGING_BYTES = 65536;    // per warp 8 KB (EW = 8: ring of 2 fp32 boxes of 32 rows x 128 B, or 4 16-bit boxes of 32 rows x 64 B) or 4 KB (EW = 16)
 
 struct GemmParams {
   int M, N, K;
@@ -237,25 +238,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&v
 // reduce-add form, so C is never read back.
 // ---------------------------------------------------------------------------------------------
 struct Stager {
-  uint8_t* base;     // this warp's 8 KB staging ring (1024-byte aligned)
+  uint8_t* base;     // this warp's staging ring (1024-byte aligned)
   int lane;
   int slot;          // next ring slot
   int wide;          // 1: 4 KB slots (some output of this epilogue is fp32), 0: 2 KB slots (all outputs 16-bit)
 };
 
+template <int EW>
 __device__ __forceinline__ void stage_and_store(Stager& s, const CUtensorMap* map, const float (&f)[32], int kind /*0 f32, 1 bf16, 2 f16*/,
                                                 bool reduce, int col0, int row0) {
   // ring of staging slots: before overwriting a slot, the bulk store that last used it must have read it out,
   // i.e. at most (slots - 1) younger stores may still be pending
+  constexpr int WIDE_SLOTS = (STAGING_BYTES / EW) / 4096, NARROW_SLOTS = (STAGING_BYTES / EW) / 2048;
   uint8_t* b;
   if (s.wide) {
     b = s.base + (s.slot << 12);
-    s.slot = (s.slot + 1) & 1;
-    if (s.lane == 0) tma_store_wait_read<1>();
+    s.slot = (s.slot + 1) & (WIDE_SLOTS - 1);
+    if (s.lane == 0) tma_store_wait_read<WIDE_SLOTS - 1>();
   } else {
     b = s.base + (s.slot << 11);
-    s.slot = (s.slot + 1) & 3;
-    if (s.lane == 0) tma_store_wait_read<3>();
+    s.slot = (s.slot + 1) & (NARROW_SLOTS - 1);
+    if (s.lane == 0) tma_store_wait_read<NARROW_SLOTS - 1>();
   }
   __syncwarp();
   const int r = s.lane;
@@ -280,6 +283,7 @@ __device__ __forceinline__ void stage_and_store(Stager& s, const CUtensorMap* ma
   }
 }
 
+template <int EW>
 __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stager& s, const CUtensorMap* mc, const CUtensorMap* mc2,
                                                       const CUtensorMap* mc3, uint32_t (&v)[32], long long row, int row0, int col0,
                                                       bool split_first) {
@@ -307,10 +311,10 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
   const bool gtanh = (p.flags & NEKO_GEMM_GELU_TANH) != 0;
   switch (p.epi) {
     case NEKO_EPI_BF16:
-      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      stage_and_store<EW>(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
       break;
     case NEKO_EPI_GELU_BF16:
-      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      stage_and_store<EW>(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
       if (gtanh) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
@@ -318,8 +322,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
       }
-      stage_and_store(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
-      if (p.C3) stage_and_store(s, mc3, f, 1, false, col0, row0);
+      stage_and_store<EW>(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
+      if (p.C3) stage_and_store<EW>(s, mc3, f, 1, false, col0, row0);
       break;
     case NEKO_EPI_DGELU_BF16: {
       if (in_rows) {
@@ -347,11 +351,11 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
             if (i < ncols) f[i] *= gtanh ? gelu_tanh_grad(__bfloat162float(a[i])) : gelu_erf_grad(__bfloat162float(a[i]));
         }
       }
-      stage_and_store(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
+      stage_and_store<EW>(s, mc, f, c_f16 ? 2 : 1, false, col0, row0);
       break;
     }
     case NEKO_EPI_F32:
-      stage_and_store(s, mc, f, 0, p.accumulate || p.splits > 1, col0, row0);
+      stage_and_store<EW>(s, mc, f, 0, p.accumulate || p.splits > 1, col0, row0);
       break;
     default: {  // NEKO_EPI_RESID_F32 / NEKO_EPI_RESID_F32_BF16
       if (p.drop.seed) {  // resid_dropout on the branch output, before the residual add
@@ -378,8 +382,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& p, Stage
             if (i < ncols) f[i] += add[i];
         }
       }
-      stage_and_store(s, mc, f, 0, false, col0, row0);
-      if (p.epi == NEKO_EPI_RESID_F32_BF16) stage_and_store(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
+      stage_and_store<EW>(s, mc, f, 0, false, col0, row0);
+      if (p.epi == NEKO_EPI_RESID_F32_BF16) stage_and_store<EW>(s, mc2, f, c2_f16 ? 2 : 1, false, col0, row0);
       break;
     }
   }
@@ -474,8 +478,8 @@ __device__ __forceinline__ void aux_combine_store(const GemmParams& p, uint8_t* 
 // stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues M=256 MMAs that read both
 // shared memories and write both tensor memories, so every operand byte crosses L2 -> SM once per PAIR instead of
 // once per CTA (the single-CTA kernel is bound by that traffic, profiles/r01_ncu_gemm_full.md).
-template <bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <bool PAIR, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
                     const __grid_constant__ CUtensorMap map_c3, const __grid_constant__ CUtensorMap map_aux, const GemmParams p) {
@@ -514,9 +518,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // pair: both CTAs' epilogues release the leader
+      mbar_init(tempty_bar(a), PAIR ? 2 * EW : EW);  // pair: both CTAs' epilogues release the leader
     }
-    for (int e = 0; e < GEMM_EPI_WARPS; ++e) {
+    for (int e = 0; e < EW; ++e) {
       mbar_init(aux_bar(e, 0), 1);
       mbar_init(aux_bar(e, 1), 1);
     }
@@ -638,9 +642,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     Stager stg;
-    const int e = warp - 2;            // 0..7
-    const int half = e >> 2;           // which half of the tile's columns
-    stg.base = staging + (size_t)e * STAGING_PER_WARP;
+    const int e = warp - 2;            // 0..EW-1
+    const int half = e >> 2;           // which part (half for EW = 8, quarter for EW = 16) of the tile's columns
+    constexpr int PARTS = EW / 4;      // column parts per TMEM lane quarter
+    stg.base = staging + (size_t)e * (STAGING_BYTES / EW);
     stg.lane = lane;
     stg.slot = 0;
     stg.wide = (p.epi == NEKO_EPI_F32 || p.epi == NEKO_EPI_RESID_F32 || p.epi == NEKO_EPI_RESID_F32_BF16) ? 1 : 0;
@@ -649,6 +654,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t aux_phase[2] = {0u, 0u};
     const bool aux_f32 = (p.epi == NEKO_EPI_RESID_F32);
     const int aux_slot_bytes = aux_f32 ? 4096 : 2048;
+    const int aux_slots = min(2, (STAGING_BYTES / EW) / aux_slot_bytes);   // 1 when a 4 KB warp region holds fp32 boxes
     for (long long u = u_first; u < units; u += u_step) {
       const long long t = u / p.splits;
       const bool split_first = (u - t * p.splits) == 0;
@@ -659,21 +665,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.tma_aux) {
         // chunks of this warp: c = half * nch + cc.  The aux boxes of the first two are requested before the accumulator
         // is complete (the main loop of this tile is still running), later ones one chunk ahead.
-        const int nch = BN / 64;
+        const int nch = BN / (32 * PARTS);
         const int c_first = half * nch;
         int n_live = 0;
         for (int cc = 0; cc < nch; ++cc) n_live += (n0 + (c_first + cc) * 32 < p.N) ? 1 : 0;
         const int row0 = m0 + q * 32;
         if (lane == 0) tma_store_wait_read<0>();     // the previous tile's stores have read both slots
         __syncwarp();
-        for (int cc = 0; cc < 2 && cc < n_live; ++cc) {
+        for (int cc = 0; cc < aux_slots && cc < n_live; ++cc) {
           if (aux_f32) aux_issue<true>(stg.base + cc * aux_slot_bytes, &map_aux, aux_bar(e, cc), lane, n0 + (c_first + cc) * 32, row0);
           else         aux_issue<false>(stg.base + cc * aux_slot_bytes, &map_aux, aux_bar(e, cc), lane, n0 + (c_first + cc) * 32, row0);
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         for (int cc = 0; cc < n_live; ++cc) {
-          const int slot = cc & 1;
+          const int slot = cc & (aux_slots - 1);
           const int col0 = n0 + (c_first + cc) * 32;
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)((c_first + cc) * 32), v);
@@ -682,23 +688,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint8_t* b = stg.base + slot * aux_slot_bytes;
           if (aux_f32) aux_combine_store<true>(p, b, &map_c, v, lane, row, row0, col0);
           else         aux_combine_store<false>(p, b, &map_c, v, lane, row, row0, col0);
-          if (cc + 2 < n_live) {     // refill this slot with the aux box of chunk cc + 2 once its store has read it out
+          if (cc + aux_slots < n_live) {     // refill this slot with the aux box of a later chunk once its store has read it out
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            if (aux_f32) aux_issue<true>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + 2) * 32, row0);
-            else         aux_issue<false>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + 2) * 32, row0);
+            if (aux_f32) aux_issue<true>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + aux_slots) * 32, row0);
+            else         aux_issue<false>(b, &map_aux, aux_bar(e, slot), lane, n0 + (c_first + cc + aux_slots) * 32, row0);
           }
         }
       } else {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        for (int cc = 0; cc < BN / 64; ++cc) {
-          const int c = half * (BN / 64) + cc;
+        const int nch = (BN / 32 + PARTS - 1) / PARTS;      // BN = 192 is launched with EW = 8 only (6 chunks / 2 parts)
+        for (int cc = 0; cc < nch; ++cc) {
+          const int c = half * nch + cc;
           const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
+          if (c * 32 >= BN || col0 >= p.N) break;  // warp-uniform
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)(c * 32), v);
-          if (p.tma_store) epilogue_chunk_staged(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
+          if (p.tma_store) epilogue_chunk_staged<EW>(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
           else if (row < p.M) epilogue_chunk(p, v, row, col0);
         }
       }
@@ -943,11 +950,19 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    const void* fns[] = {(const void*)gemm_tcgen05_kernel<false, 8>, (const void*)gemm_tcgen05_kernel<true, 8>,
+                         (const void*)gemm_tcgen05_kernel<false, 16>, (const void*)gemm_tcgen05_kernel<true, 16>};
+    for (const void* f : fns)
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
+  // epilogue warps: 16 where the epilogue, not the main loop, bounds the launch (NEKO_GEMM_EPI16=0/1 forces; BN = 192 has no
+  // 4-way column split)
+  const int epi16_env = getenv("NEKO_GEMM_EPI16") ? atoi(getenv("NEKO_GEMM_EPI16")) : -1;   // read per call: tools/gemm_sweep.py flips it
+  bool epi16 = (epilogue == NEKO_EPI_GELU_BF16);   // measured (profiles/r02_gemm_epi16_sweep.txt): 58 -> 54 us for c_fc, neutral or worse elsewhere
+  if (epi16_env >= 0) epi16 = epi16_env != 0;
+  if (p.BN == 192) epi16 = false;
+  const int threads = 64 + 32 * (epi16 ? 16 : 8);
   const long long units = mb_ * ((N + p.BN - 1) / p.BN) * p.splits;
   if (p.pair) {
     const int pairs = sms / 2;
@@ -955,7 +970,7 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute at[2];
@@ -964,11 +979,13 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ma, mb, mc, mc2, mc3, maux, p);
+    cudaError_t e = epi16 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16>, ma, mb, mc, mc2, mc3, maux, p)
+                          : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ma, mb, mc, mc2, mc3, maux, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm pair)");
   } else {
     const int grid = (int)(units < sms ? units : sms);
-    cudaError_t e = launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p);
+    cudaError_t e = epi16 ? launch_pdl(gemm_tcgen05_kernel<false, 16>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p)
+                          : launch_pdl(gemm_tcgen05_kernel<false, 8>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm)");
   }
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");

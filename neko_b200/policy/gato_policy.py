@@ -314,6 +314,7 @@ class GatoPolicy(nn.Module):
         self.head_mode = "rows"
         self.materialize_logits = True  # False: head evaluated on loss rows only, forward returns logits=None
         self.lean_logits_f16 = True     # ... and, when gradients are wanted, those logits live in fp16 between head GEMM and fused CE
+        self.mlp_proj_bf16 = False      # training forward: mlp down-projection on the bf16 activation twin (see _decoder)
         # 16-bit format of the FORWARD operands (activations fed to GEMMs, weight copy).  fp16 has 3 more mantissa
         # bits than bf16 at the same tensor-core rate and brings logits max-abs error from 2.1e-2 to ~6e-3 at
         # d=768/L=6 (DESIGN.md "precision"); gradients stay bf16 for range, the residual stream stays fp32.
@@ -1059,7 +1060,14 @@ class GatoPolicy(nn.Module):
             fpre = self._buf("fpre" + tag, (N, 4 * d), torch.bfloat16)
             fact, fact_b = pair("fact", tag, (N, 4 * d))
             fgate = None
-            if not gate:
+            # mlp_proj_bf16: the GELU GEMM is bound by its output bytes (three [N, 4d] tensors: pre-activation, fp16 activation for
+            # the forward down-projection, bf16 twin for its weight gradient).  With the flag the forward down-projection runs on
+            # the bf16 twin (and the bf16 weight copy) and the fp16 tensor is never written.
+            lowp = dual and self.mlp_proj_bf16 and not gate
+            if lowp:
+                ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact_b,
+                         bias=blk.mlp.c_fc.bias, gelu_tanh=self._gelu_tanh)
+            elif not gate:
                 ops.gemm(ln2, self._wview(pre + "mlp.c_fc.weight"), b_mn=True, epilogue=ops.EPI_GELU_BF16, out=fpre, out2=fact,
                          out3=fact_b if dual else None, bias=blk.mlp.c_fc.bias, gelu_tanh=self._gelu_tanh)
             else:   # geglu: h = gelu(c_fc(x)) * gated_layer(x)   (trajectory_gpt2.py:267-276; nn.Linear weight is [out, in])
@@ -1072,8 +1080,8 @@ class GatoPolicy(nn.Module):
                 ops.geglu_fwd(gelu_o, fgate, fact, fact_b if dual else None)
                 self.launches += 2
             x2 = self._buf(f"x.{2 * i + 2}" if keep else "x.a", (N, d), torch.float32)
-            ops.gemm(fact, self._wview(pre + "mlp.c_proj.weight"), b_mn=True, epilogue=ops.EPI_RESID_F32, out=x2, aux=x1,
-                     bias=blk.mlp.c_proj.bias, drop=self._drop_site(st, 4 * i + 3, blk.mlp.dropout.p))
+            ops.gemm(fact_b if lowp else fact, self._wview(pre + "mlp.c_proj.weight", bwd=lowp), b_mn=True, epilogue=ops.EPI_RESID_F32,
+                     out=x2, aux=x1, bias=blk.mlp.c_proj.bias, drop=self._drop_site(st, 4 * i + 3, blk.mlp.dropout.p))
             self.launches += 7
             if keep:
                 acts.append((x, ln1_b, m1, r1, qkv, att_b, lse, x1, ln2_b, m2, r2, fpre, fact_b, fgate))
@@ -1132,7 +1140,7 @@ class GatoPolicy(nn.Module):
         p = st.plan
         return (p.B, p.seq_len, p.width, p.descs.tobytes(), tuple((g.height, g.width, g.is_u8, g.n_frames) for g in p.image_groups),
                 len(p.precomputed_patch), st.compute_loss, st.need_grad, self.training, self.materialize_logits, self.head_mode,
-                self.fwd_dtype, st.row_bins is not None, self._dropout_ps(), self.lean_logits_f16)
+                self.fwd_dtype, st.row_bins is not None, self._dropout_ps(), self.lean_logits_f16, self.mlp_proj_bf16)
 
     def _engine_forward(self, st: _State):
         if not self.use_cuda_graphs:

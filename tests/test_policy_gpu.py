@@ -378,6 +378,8 @@ def test_model_scale_parity(golden_dir, name, mode):
     cfg = O.GatoConfig(**O.CONFIGS[name])
     w = O.make_weights(cfg, seed=0, perturb=False)
     m = make_policy(cfg, w, train=(mode == "train"))
+    if os.environ.get("NEKO_MLP_PROJ_BF16") is not None:      # experiment switch (DESIGN.md section 4 "precision")
+        m.mlp_proj_bf16 = os.environ["NEKO_MLP_PROJ_BF16"] == "1"
     batch = scale_batch(name)
     torch.manual_seed(77)
     logits, loss = m(batch, compute_loss=True)
