@@ -222,10 +222,14 @@ class GradSynchronizer:
         if self._cuda:
             if self._p2p is not None and self._p2p.proto == "ce":
                 self._p2p.ce_flush(self._stream)
-            if self._nccl_used:
-                torch.cuda.current_stream(self.arena.device).wait_stream(self._nccl_stream)
-                self._nccl_used = False
-            torch.cuda.current_stream(self.arena.device).wait_stream(self._stream)
+            self._join_streams()
+
+    def _join_streams(self):
+        """The compute stream waits for every stream an exchange of this step ran on."""
+        if self._nccl_used:
+            torch.cuda.current_stream(self.arena.device).wait_stream(self._nccl_stream)
+            self._nccl_used = False
+        torch.cuda.current_stream(self.arena.device).wait_stream(self._stream)
 
     def begin_step(self):
         self.launched = []

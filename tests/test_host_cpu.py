@@ -285,3 +285,71 @@ def test_vendored_reference_recipe(tmp_path):
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
     # oracle/_ref must stay out of the history
     assert "oracle/_ref/" in open(os.path.join(ROOT, ".gitignore")).read()
+
+
+def test_copy_engine_bucket_schedule_covers_the_arena_once():
+    """Host logic of the copy-engine data-parallel exchange (neko_b200/dp.py) with the device side mocked out: the groups handed to
+    ce_submit cover every live arena element exactly once, leave the skip ranges out, respect the bucket size, are drained in
+    submission order with non-decreasing ticks, and ranges that complete near the end of backward are not held back."""
+    import torch
+    from neko_b200.dp import GradSynchronizer
+
+    class FakeP2P:
+        proto = "ce"
+
+        def __init__(self):
+            self.submitted, self.drains, self.flushed = [], [], 0
+
+        def begin_step(self):
+            pass
+
+        def ce_submit(self, ranges, scale, comm, tick=0):
+            self.submitted.append((list(ranges), scale, tick))
+
+        def ce_drain(self, comm, tick=None, min_age=2):
+            self.drains.append(tick)
+
+        def ce_flush(self, comm):
+            self.flushed += 1
+
+    total = 10_000_000
+    arena = torch.zeros(total)
+    s = GradSynchronizer(arena, bucket_bytes=4 * 1_000_000)          # world size 1 without a process group ...
+    s.world, s._cuda, s.backend, s._p2p = 4, True, "p2p", FakeP2P()   # ... pretend: 4 ranks, CUDA, own exchange
+    s._join_streams = lambda: None
+    s.tail_elems = 600_000
+    s.skip_ranges = [(7_000_000, 9_700_000), (9_999_000, total)]
+    # completion order of a backward: one big head, six "layers" of uneven size, then the tail that contains the skipped rows
+    notes = [(0, 3_500_000)] + [(3_500_000 + 500_000 * k, 4_000_000 + 500_000 * k) for k in range(6)] + [(6_500_000, total)]
+    s.begin_step()
+    for lo, hi in notes:
+        s.on_range_ready(lo, hi)
+    s.finish()
+    p2p = s._p2p
+    flat = [r for grp, _sc, _t in p2p.submitted for r in grp]
+    covered = torch.zeros(total, dtype=torch.int32)
+    for lo, hi in flat:
+        assert lo % 4 == 0 and hi % 4 == 0 and hi > lo
+        covered[lo:hi] += 1
+    live = torch.ones(total, dtype=torch.int32)
+    for lo, hi in s.skip_ranges:
+        live[lo:hi] = 0
+    assert torch.equal(covered, live)
+    assert all(sum(b - a for a, b in grp) <= s.bucket_elems for grp, _sc, _t in p2p.submitted)
+    assert all(abs(sc - 0.25) < 1e-12 for _g, sc, _t in p2p.submitted)
+    ticks = [t for _g, _sc, t in p2p.submitted]
+    assert ticks == sorted(ticks) and p2p.drains == sorted(p2p.drains) and p2p.flushed == 1
+    # the head is cut into bucket-sized exchanges at once; the last layer is submitted at its own notification, not at finish()
+    assert p2p.submitted[0][0] == [(0, 1_000_000)] and ticks[0] == 1
+    last_layer = next(t for g, _sc, t in p2p.submitted if (6_000_000, 6_500_000) in g or any(a <= 6_000_000 < b for a, b in g))
+    assert last_layer == 7 and len(notes) == 8
+    # the small live ranges of the tail share one exchange
+    assert any(len(g) > 1 for g, _sc, _t in p2p.submitted)
+    # no_sync: nothing is submitted
+    n = len(p2p.submitted)
+    with s.no_sync():
+        s.begin_step()
+        for lo, hi in notes:
+            s.on_range_ready(lo, hi)
+        s.finish()
+    assert len(p2p.submitted) == n
