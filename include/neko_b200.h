@@ -166,9 +166,15 @@ typedef struct neko_gemm_desc {
   const float* bias;            /* [N] or NULL                                                  */
   const void* aux; int64_t ld_aux;
   neko_dropout drop;            /* RESID epilogues: C = aux + dropout(acc + bias) (resid_dropout, trajectory_gpt2.py:254,278) */
+  void* workspace;              /* optional, zero-initialised ONCE by the caller and then left to the library: lets launches whose  */
+  int64_t workspace_bytes;      /* tile count is a poor multiple of the SM count run stream-K (a tile's k-range shared by two CTAs /
+                                 * CTA pairs, partial accumulators and their counters live here).  neko_gemm_workspace_bytes() is
+                                 * enough for any problem; NULL / too small = classic tile scheduling.  One workspace per stream. */
 } neko_gemm_desc;
 
 int neko_gemm(const neko_gemm_desc* host_desc, void* stream);
+/* Bytes of neko_gemm_desc.workspace that cover every problem on this device (148 partial 128 x 256 fp32 tiles + counters). */
+int64_t neko_gemm_workspace_bytes(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Causal self-attention with left padding (Attention._attn, trajectory_gpt2.py:163-188, with the

@@ -52,7 +52,7 @@ class GemmDesc(C.Structure):
                 ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64),
                 ("C", C.c_void_p), ("ldc", C.c_int64), ("C2", C.c_void_p), ("ldc2", C.c_int64),
                 ("C3", C.c_void_p), ("ldc3", C.c_int64), ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_aux", C.c_int64),
-                ("drop", Dropout)]
+                ("drop", Dropout), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID_F32, EPI_DGELU_BF16, EPI_RESID_F32_BF16 = range(6)
@@ -78,7 +78,9 @@ def load():
     lib.neko_last_error.restype = C.c_char_p
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch
-        if name != "neko_last_error":
+        if name == "neko_gemm_workspace_bytes":
+            fn.restype = C.c_int64
+        elif name != "neko_last_error":
             fn.restype = C.c_int
     _lib = lib
     return lib

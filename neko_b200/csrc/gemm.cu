@@ -62,6 +62,9 @@ struct GemmParams {
   int pair;        // 1: cta_group::2 CTA pairs (256 x BN tile per pair)
   int tma_store;   // outputs leave through shared-memory staging + cp.async.bulk.tensor stores
   int tma_aux;     // RESID_F32 / DGELU: the auxiliary operand arrives as TMA boxes in the staging ring (prefetched, coalesced)
+  int streamk;     // 1: the (tile, k-block) space is cut into one contiguous range per worker (see WorkIter)
+  float* sk_acc;   // stream-K: partial accumulators, [workers][TM][BN] fp32
+  unsigned* sk_flags;  // stream-K: [workers] arrival counters, then [workers] consumer counters (zero between launches)
   int kb_per_split;
   DropCfg drop;    // RESID epilogues: C = aux + dropout(acc + bias)
 };
@@ -478,11 +481,76 @@ __device__ __forceinline__ void aux_combine_store(const GemmParams& p, uint8_t* 
 // stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues M=256 MMAs that read both
 // shared memories and write both tensor memories, so every operand byte crosses L2 -> SM once per PAIR instead of
 // once per CTA (the single-CTA kernel is bound by that traffic, profiles/r01_ncu_gemm_full.md).
+// stream-K owner: add the helper's partial accumulator (this thread's row, 32 columns from `col`) to the freshly loaded chunk
+__device__ __forceinline__ void sk_add_partial(uint32_t (&v)[32], const float* sk_row, int col) {
+  const float4* p4 = reinterpret_cast<const float4*>(sk_row + col);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 a = __ldcg(p4 + j);   // written by another SM during this launch: L2, never a stale L1 line
+    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + a.x);
+    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + a.y);
+    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + a.z);
+    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + a.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Work distribution.  Classic: worker w takes units w, w + W, ... of the (tile, k-split) list.  Stream-K (p.streamk): the
+// linearised (tile, k-block) space is cut into W contiguous ranges of (almost) equal length, so a launch whose tile count is
+// 1.2 x the worker count costs 1.2 rounds of main loop instead of 2.  The host enables it only when every range is at least one
+// tile long; a tile is then shared by at most two workers: worker w ENDS with the head k-blocks of a tile (kind 2: it owns the
+// tile and runs the epilogue) and worker w + 1 STARTS with its tail k-blocks (kind 1: it stores the raw partial accumulator into
+// workspace slot w + 1 and signals).  The helper does its part first and the owner last, so the owner practically never waits.
+// ---------------------------------------------------------------------------------------------
+struct Work {
+  long long tile;
+  int kb0, kb1;
+  int kind;          // 0 whole tile / k-split unit, 1 helper (partial -> workspace), 2 owner (adds the next worker's partial)
+  bool split_first;
+};
+struct WorkIter {
+  long long u, u_step, units;      // classic
+  int splits, kb_per_split, k_blocks;
+  long long lin, end;              // stream-K
+  int streamk;
+  __device__ __forceinline__ WorkIter(const GemmParams& p, long long worker, long long workers, long long tiles, int kblocks)
+      : u(worker), u_step(workers), units(tiles * p.splits), splits(p.splits), kb_per_split(p.kb_per_split), k_blocks(kblocks),
+        lin(0), end(0), streamk(p.streamk) {
+    if (streamk) {
+      const long long total = tiles * (long long)kblocks;
+      lin = worker * total / workers;
+      end = (worker + 1) * total / workers;
+    }
+  }
+  __device__ __forceinline__ bool next(Work& w) {
+    if (!streamk) {
+      if (u >= units) return false;
+      w.tile = u / splits;
+      const int ks = (int)(u - w.tile * splits);
+      w.kb0 = ks * kb_per_split;
+      w.kb1 = min(k_blocks, w.kb0 + kb_per_split);
+      w.kind = 0;
+      w.split_first = ks == 0;
+      u += u_step;
+      return true;
+    }
+    if (lin >= end) return false;
+    w.tile = lin / k_blocks;
+    w.kb0 = (int)(lin - w.tile * k_blocks);
+    w.kb1 = (int)min((long long)k_blocks, (long long)w.kb0 + (end - lin));
+    w.kind = (w.kb0 > 0) ? 1 : (w.kb1 < k_blocks ? 2 : 0);
+    w.split_first = true;
+    lin += w.kb1 - w.kb0;
+    return true;
+  }
+};
+
 template <bool PAIR, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
-                    const __grid_constant__ CUtensorMap map_c3, const __grid_constant__ CUtensorMap map_aux, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap map_c3, const __grid_constant__ CUtensorMap map_aux,
+                    const __grid_constant__ CUtensorMap map_ws, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -556,12 +624,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u_first; u < units; u += u_step) {
-        const long long t = u / p.splits;
-        const int ks = (int)(u - t * p.splits);
+      WorkIter it(p, u_first, u_step, tiles, k_blocks);
+      Work w;
+      while (it.next(w)) {
+        const long long t = w.tile;
         const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * TM + (int)rank * BM;   // this CTA's 128 rows
         const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN + (int)rank * BNL;  // this CTA's slice of B
-        const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+        const int kb0 = w.kb0, kb1 = w.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -611,9 +680,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long u = u_first; u < units; u += u_step) {
-        const int ks = (int)(u % p.splits);
-        const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+      WorkIter it(p, u_first, u_step, tiles, k_blocks);
+      Work w;
+      while (it.next(w)) {
+        const int kb0 = w.kb0, kb1 = w.kb1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -655,14 +725,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool aux_f32 = (p.epi == NEKO_EPI_RESID_F32);
     const int aux_slot_bytes = aux_f32 ? 4096 : 2048;
     const int aux_slots = min(2, (STAGING_BYTES / EW) / aux_slot_bytes);   // 1 when a 4 KB warp region holds fp32 boxes
-    for (long long u = u_first; u < units; u += u_step) {
-      const long long t = u / p.splits;
-      const bool split_first = (u - t * p.splits) == 0;
+    WorkIter it(p, u_first, u_step, tiles, k_blocks);
+    Work w;
+    const unsigned sk_total = (unsigned)(EW * (PAIR ? 2 : 1));     // epilogue warps that store / consume one partial tile
+    while (it.next(w)) {
+      const long long t = w.tile;
+      const bool split_first = w.split_first;
       const int m0 = (int)(p.n_fast ? (t / n_blocks) : (t % m_blocks)) * TM + (int)rank * BM;
       const int n0 = (int)(p.n_fast ? (t % n_blocks) : (t / m_blocks)) * BN;
       const long long row = (long long)m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      if (p.tma_aux) {
+      // stream-K: rows of this thread / warp inside workspace slot `sk_slot` ([TM][BN] fp32 per slot)
+      const long long sk_slot = (w.kind == 1) ? u_first : u_first + 1;
+      const float* sk_row = (w.kind == 2) ? p.sk_acc + ((sk_slot * TM + (long long)rank * BM + q * 32 + lane) * BN) : nullptr;
+      if (w.kind == 1) {
+        // helper: the raw accumulator of this k-range goes to the workspace as fp32 boxes, then one arrival per warp
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (lane == 0) tma_store_wait_read<0>();        // nothing of an earlier epilogue may still read the staging region
+        __syncwarp();
+        const int nchh = (BN / 32 + PARTS - 1) / PARTS;
+        for (int cc = 0; cc < nchh; ++cc) {
+          const int c = half * nchh + cc;
+          if (c * 32 >= BN) break;
+          uint32_t v[32];
+          tc_ld32(taddr + (uint32_t)(c * 32), v);
+          uint8_t* b = stg.base;                        // one 4 KB fp32 box at a time
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(b + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_ws, smem_u32(b), c * 32, (int)(sk_slot * TM) + (int)rank * BM + q * 32);
+            tma_store_commit();
+          }
+        }
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the partial is in global memory ...
+          __threadfence();
+          atomicAdd(p.sk_flags + sk_slot, 1u);                         // ... before the owner is told
+        }
+        __syncwarp();
+      } else if (p.tma_aux) {
         // chunks of this warp: c = half * nch + cc.  The aux boxes of the first two are requested before the accumulator
         // is complete (the main loop of this tile is still running), later ones one chunk ahead.
         const int nch = BN / (32 * PARTS);
@@ -678,11 +786,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
+        if (w.kind == 2) {      // owner: the helper's partial must have landed
+          if (lane == 0) {
+            while (*reinterpret_cast<volatile unsigned*>(p.sk_flags + sk_slot) < sk_total) __nanosleep(32);
+            __threadfence();
+          }
+          __syncwarp();
+        }
         for (int cc = 0; cc < n_live; ++cc) {
           const int slot = cc & (aux_slots - 1);
           const int col0 = n0 + (c_first + cc) * 32;
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)((c_first + cc) * 32), v);
+          if (sk_row) sk_add_partial(v, sk_row, (c_first + cc) * 32);
           mbar_wait(aux_bar(e, slot), aux_phase[slot]);
           aux_phase[slot] ^= 1u;
           uint8_t* b = stg.base + slot * aux_slot_bytes;
@@ -698,6 +814,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       } else {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
+        if (w.kind == 2) {      // owner: the helper's partial must have landed
+          if (lane == 0) {
+            while (*reinterpret_cast<volatile unsigned*>(p.sk_flags + sk_slot) < sk_total) __nanosleep(32);
+            __threadfence();
+          }
+          __syncwarp();
+        }
         const int nch = (BN / 32 + PARTS - 1) / PARTS;      // BN = 192 is launched with EW = 8 only (6 chunks / 2 parts)
         for (int cc = 0; cc < nch; ++cc) {
           const int c = half * nch + cc;
@@ -705,8 +828,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (c * 32 >= BN || col0 >= p.N) break;  // warp-uniform
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)(c * 32), v);
+          if (sk_row) sk_add_partial(v, sk_row, c * 32);
           if (p.tma_store) epilogue_chunk_staged<EW>(p, stg, &map_c, &map_c2, &map_c3, v, row, m0 + q * 32, col0, split_first);
           else if (row < p.M) epilogue_chunk(p, v, row, col0);
+        }
+      }
+      if (w.kind == 2) {        // the last consumer of a partial tile re-arms its counters for the next launch
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned prev = atomicAdd(p.sk_flags + u_step + sk_slot, 1u);
+          if (prev == sk_total - 1u) {
+            p.sk_flags[u_step + sk_slot] = 0u;
+            p.sk_flags[sk_slot] = 0u;
+            __threadfence();
+          }
         }
       }
       tc_fence_before();
@@ -803,6 +938,11 @@ int make_map(CUtensorMap* out, const void* ptr, unsigned long long inner, unsign
 }
 
 }  // namespace neko
+
+extern "C" int64_t neko_gemm_workspace_bytes(void) {
+  // 148 workers x (128 x 256 fp32) = 74 pair tiles of 256 x 256: partial accumulators, then 2 x 148 counters, rounded up
+  return (int64_t)neko::sm_count() * 128 * 256 * 4 + 4096;
+}
 
 extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   using namespace neko;
@@ -939,6 +1079,31 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
       if (rc != NEKO_OK) return rc;
     }
   }
+  // stream-K (see WorkIter): worth it when the tile count is a poor multiple of the worker count -- the N = 768 projections and
+  // dgrads at the cfg2 token count run 90 pair tiles on 74 pairs, i.e. two rounds for 1.2 rounds of work
+  CUtensorMap mws;
+  memset(&mws, 0, sizeof(mws));
+  p.streamk = 0; p.sk_acc = nullptr; p.sk_flags = nullptr;
+  {
+    const long long workers = p.pair ? sms / 2 : sms;
+    const long long tiles_sk = mb_ * ((N + p.BN - 1) / p.BN);
+    const long long tm = p.pair ? 2 * BM : BM;
+    const long long rounds = (tiles_sk + workers - 1) / workers;
+    const long long acc_bytes = workers * tm * p.BN * 4;
+    const long long need = acc_bytes + 2 * workers * 4;
+    const int sk_env = getenv("NEKO_GEMM_STREAMK") ? atoi(getenv("NEKO_GEMM_STREAMK")) : -1;
+    bool want = p.splits == 1 && p.tma_store && epilogue != NEKO_EPI_F32 && p.BN != 192 && tiles_sk >= workers && kblocks >= 8 &&
+                tiles_sk % workers != 0 && (double)(rounds * workers) >= 1.12 * (double)tiles_sk && rounds <= 4;
+    if (sk_env == 0) want = false;
+    if (sk_env < 0) want = false;          // default off until measured (NEKO_GEMM_STREAMK=1 enables)
+    if (want && gd->workspace && gd->workspace_bytes >= need && (reinterpret_cast<uintptr_t>(gd->workspace) & 127) == 0) {
+      p.sk_acc = static_cast<float*>(gd->workspace);
+      p.sk_flags = reinterpret_cast<unsigned*>(static_cast<char*>(gd->workspace) + acc_bytes);
+      rc = make_map(&mws, p.sk_acc, (unsigned long long)p.BN, (unsigned long long)(workers * tm), (unsigned long long)p.BN, 32, 32, 2);
+      if (rc != NEKO_OK) return rc;
+      p.streamk = 1;
+    }
+  }
   if (!p.a_mn) rc = make_map(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, BK, BM, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
   else         rc = make_map(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, BK, (flags & NEKO_GEMM_A_F16) ? 1 : 0);
   if (rc != NEKO_OK) return rc;
@@ -963,7 +1128,7 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
   if (epi16_env >= 0) epi16 = epi16_env != 0;
   if (p.BN == 192) epi16 = false;
   const int threads = 64 + 32 * (epi16 ? 16 : 8);
-  const long long units = mb_ * ((N + p.BN - 1) / p.BN) * p.splits;
+  const long long units = mb_ * ((N + p.BN - 1) / p.BN) * p.splits;   // stream-K: tiles >= workers, so the grid below is the full one
   if (p.pair) {
     const int pairs = sms / 2;
     const int grid = 2 * (int)(units < pairs ? units : pairs);
@@ -979,13 +1144,13 @@ extern "C" int neko_gemm(const neko_gemm_desc* gd, void* stream) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = epi16 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16>, ma, mb, mc, mc2, mc3, maux, p)
-                          : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ma, mb, mc, mc2, mc3, maux, p);
+    cudaError_t e = epi16 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16>, ma, mb, mc, mc2, mc3, maux, mws, p)
+                          : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ma, mb, mc, mc2, mc3, maux, mws, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm pair)");
   } else {
     const int grid = (int)(units < sms ? units : sms);
-    cudaError_t e = epi16 ? launch_pdl(gemm_tcgen05_kernel<false, 16>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p)
-                          : launch_pdl(gemm_tcgen05_kernel<false, 8>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, p);
+    cudaError_t e = epi16 ? launch_pdl(gemm_tcgen05_kernel<false, 16>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, mws, p)
+                          : launch_pdl(gemm_tcgen05_kernel<false, 8>, dim3(grid), dim3(threads), smem, as_stream(stream), ma, mb, mc, mc2, mc3, maux, mws, p);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(gemm)");
   }
   NEKO_LAUNCH_CHECK("gemm_tcgen05_kernel");

@@ -33,6 +33,21 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_GEMM_WS = {}   # device index -> zero-initialised workspace of the stream-K launches (include/neko_b200.h: neko_gemm_desc.workspace).
+# One per device: the GEMMs of a process run on one stream at a time (eager steps and graph replays never overlap).
+
+
+def _gemm_workspace(device):
+    key = device.index
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                   # first use inside a capture: no allocation there, this launch runs the classic schedule
+        ws = torch.zeros(int(load().neko_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
          out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, out3: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, accumulate: bool = False,
@@ -68,6 +83,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                   bias=_ptr(bias), aux=_ptr(aux), ld_aux=aux.stride(0) if aux is not None else 0)
     if drop is not None:   # RESID epilogues: C = aux + dropout(acc + bias)
         gd.drop = drop
+    ws = _gemm_workspace(a.device)
+    if ws is not None:
+        gd.workspace, gd.workspace_bytes = ws.data_ptr(), ws.numel()
     if GEMM_TIMING is not None:  # bench.py: CUDA events around every tensor-core launch (roofline.achieved)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

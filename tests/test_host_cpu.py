@@ -51,16 +51,16 @@ def test_struct_layouts_match_header(tmp_path):
     assert ctypes.sizeof(SampleDesc) == 64
     assert ctypes.sizeof(TokParams) == 40
     assert ctypes.sizeof(Dropout) == 24
-    assert ctypes.sizeof(GemmDesc) == 8 * 4 + 13 * 8 + 24
+    assert ctypes.sizeof(GemmDesc) == 8 * 4 + 13 * 8 + 24 + 16
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "neko_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "neko_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu",'
                    'sizeof(neko_sample_desc), sizeof(neko_tok_params), sizeof(neko_dropout), sizeof(neko_gemm_desc),'
-                   'offsetof(neko_gemm_desc, drop), offsetof(neko_gemm_desc, aux));return 0;}\n')
+                   'offsetof(neko_gemm_desc, drop), offsetof(neko_gemm_desc, aux), offsetof(neko_gemm_desc, workspace));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert got == [ctypes.sizeof(SampleDesc), ctypes.sizeof(TokParams), ctypes.sizeof(Dropout), ctypes.sizeof(GemmDesc),
-                   GemmDesc.drop.offset, GemmDesc.aux.offset]
+                   GemmDesc.drop.offset, GemmDesc.aux.offset, GemmDesc.workspace.offset]
 
 
 def test_no_cpu_fallback():

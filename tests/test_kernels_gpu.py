@@ -131,6 +131,38 @@ def test_gemm_epilogues(ops):
     assert (out.float() - acc * p.grad).abs().max().item() < 0.1
 
 
+@pytest.mark.parametrize("M,N,K,pair", [(7680, 768, 3072, 1), (7680, 768, 768, 0), (7680, 768, 2304, 1), (5000, 768, 1024, 0)])
+def test_gemm_stream_k(ops, monkeypatch, M, N, K, pair):
+    """Stream-K scheduling (csrc/gemm.cu WorkIter): a tile's k-range shared by two workers through the workspace.  The decoder's
+    N = 768 launches at the cfg2 token count (90 pair tiles on 74 pairs) with every epilogue that takes part, against fp32 torch and
+    against the classic schedule; twice in a row (the counters re-arm themselves)."""
+    monkeypatch.setenv("NEKO_GEMM_PAIR", str(pair))
+    a = _rand((M, K), 3, 0.5, torch.bfloat16)
+    b = _rand((N, K), 4, 0.5, torch.bfloat16)
+    bias = _rand((N,), 5)
+    resid = _rand((M, N), 6)
+    pre = _rand((M, N), 7, 1.0, torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    tol = 2e-3 * (K / 192) ** 0.5
+    outs = {}
+    for sk in ("0", "1", "1"):
+        monkeypatch.setenv("NEKO_GEMM_STREAMK", sk)
+        o16 = ops.gemm(a, b, epilogue=ops.EPI_BF16, bias=bias)
+        x = resid.clone()
+        o32 = ops.gemm(a, b, epilogue=ops.EPI_RESID_F32, bias=bias, aux=x, out=x)
+        od = ops.gemm(a, b, epilogue=ops.EPI_DGELU_BF16, aux=pre)
+        torch.cuda.synchronize()
+        assert (o32 - (ref + bias + resid)).abs().max().item() < tol, sk
+        assert (o16.float() - (ref + bias)).abs().max().item() < 0.01 * (ref + bias).abs().max().item() + 0.05, sk
+        outs.setdefault(sk, []).append((o16.clone(), o32.clone(), od.clone()))
+    c0 = outs["0"][0]
+    for c1 in outs["1"]:
+        assert (c0[1] - c1[1]).abs().max().item() < tol            # different summation order, same result within fp32 rounding
+        assert (c0[0].float() - c1[0].float()).abs().max().item() <= 0.02 * c0[0].float().abs().max().item()
+        assert (c0[2].float() - c1[2].float()).abs().max().item() <= 0.02 * c0[2].float().abs().max().item() + 1e-3
+    assert torch.equal(outs["1"][0][1], outs["1"][1][1])        # deterministic: partials are added in a fixed order
+
+
 def test_gemm_gelu_tanh_epilogues(ops):
     """gelu_new (tanh form, pretrained GPT-2: gato_policy.py:79-95) in the GELU / GELU' epilogues.  The two GELU forms differ by
     < 5e-4, below one 16-bit ulp, so the check is statistical: with B = I the pre-activation is exact, rounding errors average

@@ -116,7 +116,7 @@ if __name__ == "__main__":
     for name, flops, fn in cases():
         cells = []
         for _vn, env in VARIANTS + EXTRA:
-            for k in ("NEKO_GEMM_PAIR", "NEKO_GEMM_BN", "NEKO_GEMM_SPLITS", "NEKO_GEMM_NFAST", "NEKO_GEMM_DIRECT_STORE", "NEKO_GEMM_EPI16"):
+            for k in ("NEKO_GEMM_PAIR", "NEKO_GEMM_BN", "NEKO_GEMM_SPLITS", "NEKO_GEMM_NFAST", "NEKO_GEMM_DIRECT_STORE", "NEKO_GEMM_EPI16", "NEKO_GEMM_STREAMK"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             try:

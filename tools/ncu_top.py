@@ -33,7 +33,7 @@ body = rows[s + 2:e]
 isamp, isrc = h.index("# Samples"), h.index("Source")
 tot = sum(int(r[isamp] or 0) for r in body) or 1
 print(f"  top stalled SASS lines of {len(body)} ({tot} samples):")
-for r in sorted(body, key=lambda r: -int(r[isamp] or 0))[:16]:
+for r in sorted(body, key=lambda r: -int(r[isamp] or 0))[:28]:
     stalls = {hh: r[i] for i, hh in enumerate(h) if hh.startswith("stall_") and "(Not" not in hh and r[i] not in ("", "0")}
     best = sorted(stalls.items(), key=lambda kv: -float(kv[1]))[:2]
     print(f"   {100 * int(r[isamp]) / tot:5.1f}%  {r[isrc][:64]:64s} {best}")
