@@ -258,7 +258,14 @@ def front_end_roofline(model, host_batch, dev, cfgd, cfg_name):
             if reps is None:
                 reps = max(1, -(-(1 << 30) // (plan.n_valid_tokens * (d * 8 + 20))))
                 reps = min(reps, 64)
-                batch = batch * reps
+                base = batch
+                batch = []
+                for r in range(reps):      # text replicas get fresh ids: the scaled batch must not shrink to one L2-resident set of rows
+                    for smp in base:
+                        if r and isinstance(smp.get("text"), (list, torch.Tensor)) and "images" not in smp:
+                            n_ids = len(smp["text"]) if isinstance(smp["text"], list) else int(smp["text"].numel())
+                            smp = dict(smp, text=np.random.RandomState(1000 + r).randint(0, 50257, size=(n_ids,)).tolist())
+                        batch.append(smp)
             st = model._plan(batch, False)
             st.need_grad = False
             model._embed(st)     # uploads, image stack, first launch
