@@ -261,10 +261,10 @@ def front_end_roofline(model, host_batch, dev, cfgd, cfg_name):
                 base = batch
                 batch = []
                 for r in range(reps):      # text replicas get fresh ids: the scaled batch must not shrink to one L2-resident set of rows
-                    for smp in base:
+                    for si, smp in enumerate(base):
                         if r and isinstance(smp.get("text"), (list, torch.Tensor)) and "images" not in smp:
                             n_ids = len(smp["text"]) if isinstance(smp["text"], list) else int(smp["text"].numel())
-                            smp = dict(smp, text=np.random.RandomState(1000 + r).randint(0, 50257, size=(n_ids,)).tolist())
+                            smp = dict(smp, text=np.random.RandomState(1000 + 997 * r + si).randint(0, 50257, size=(n_ids,)).tolist())
                         batch.append(smp)
             st = model._plan(batch, False)
             st.need_grad = False
