@@ -5,8 +5,8 @@ It exists so that (1) ``oracle/make_golden.py`` can run the real reference on se
 write the fixtures under ``tests/golden/`` and (2) ``tests/test_oracle_vs_reference.py`` can
 pin the restatement in ``oracle/gato_oracle.py`` against the reference whenever
 ``/root/reference`` is mounted (it is NOT mounted on the GPU box) and (3) ``bench.py --impl reference`` /
-``cpu_baseline`` can time the reference's own CPU path on the GPU box from the git-ignored copy that
-``oracle/build_ref.py`` places under ``oracle/_ref/``.
+``cpu_baseline`` can time the reference's own CPU path on the GPU box from the git-ignored archive
+(``oracle/_ref/gato_ref.zip``, unpacked into a scratch directory of the process) that ``oracle/build_ref.py`` builds.
 
 The reference was written for transformers 4.30.2 / torch 2.0.1 (``env.yml:8-36``); this image
 has transformers 5.x and lacks gymnasium, so a handful of in-memory shims are installed before
@@ -20,14 +20,29 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-VENDORED_ROOT = os.path.join(_HERE, "_ref")     # written by oracle/build_ref.py (git-ignored; travels to the GPU box)
+VENDORED_ROOT = os.path.join(_HERE, "_ref", "gato_ref.zip")     # written by oracle/build_ref.py (git-ignored; travels to the GPU box)
+
+
+def _has_reference(root) -> bool:
+    """A directory with gato/policy/gato_policy.py, or a zip archive with that member."""
+    if not root:
+        return False
+    if os.path.isdir(root):
+        return os.path.isfile(os.path.join(root, "gato", "policy", "gato_policy.py"))
+    if os.path.isfile(root) and root.endswith(".zip"):
+        import zipfile
+        try:
+            with zipfile.ZipFile(root) as z:
+                return "gato/policy/gato_policy.py" in z.namelist()
+        except zipfile.BadZipFile:
+            return False
+    return False
 
 
 def _find_root() -> str:
-    """The mounted reference if there is one, else the copy oracle/build_ref.py placed under oracle/_ref/."""
-    cands = [os.environ.get("NEKO_REFERENCE_ROOT"), "/root/reference", VENDORED_ROOT]
-    for c in cands:
-        if c and os.path.isfile(os.path.join(c, "gato", "policy", "gato_policy.py")):
+    """The mounted reference if there is one, else the archive oracle/build_ref.py placed under oracle/_ref/."""
+    for c in (os.environ.get("NEKO_REFERENCE_ROOT"), "/root/reference", VENDORED_ROOT):
+        if _has_reference(c):
             return c
     return os.environ.get("NEKO_REFERENCE_ROOT", "/root/reference")
 
@@ -36,7 +51,7 @@ REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "gato", "policy", "gato_policy.py"))
+    return _has_reference(REFERENCE_ROOT)
 
 
 def reference_kind() -> str:
@@ -133,8 +148,21 @@ def install_shims() -> None:
 
     transformers.AutoTokenizer = _AutoTok
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = REFERENCE_ROOT
+    if os.path.isfile(root) and root.endswith(".zip"):
+        # the vendored archive: unpack into a scratch directory of this process (transformers 5 opens the source file of a model
+        # class, which zipimport cannot serve); nothing is written into the repository tree
+        import atexit
+        import shutil
+        import tempfile
+        import zipfile
+        scratch = tempfile.mkdtemp(prefix="neko_ref_")
+        atexit.register(shutil.rmtree, scratch, ignore_errors=True)
+        with zipfile.ZipFile(root) as z:
+            z.extractall(scratch)
+        root = scratch
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
     import gato.transformers.trajectory_gpt2 as tg
 

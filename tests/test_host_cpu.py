@@ -266,22 +266,26 @@ def test_plan_matches_oracle_on_random_mixed_batches(seed):
 
 
 def test_vendored_reference_recipe(tmp_path):
-    """oracle/build_ref.py: the copy under oracle/_ref/ is byte-identical to the mounted reference's path files and imports
-    through the shims (what bench.py --impl reference uses on the GPU box)."""
-    import hashlib
-    from oracle import build_ref, ref_shim
+    """oracle/build_ref.py: the archive under oracle/_ref/ holds the mounted reference's path files byte for byte (no loose reference
+    source in the tree) and imports through the shims (what bench.py --impl reference uses on the GPU box)."""
+    import zipfile
+    from oracle import build_ref
     if not os.path.isdir("/root/reference/gato"):
         pytest.skip("no /root/reference in this container")
     assert build_ref.build()
-    for rel in build_ref.FILES:
-        src = os.path.join("/root/reference", rel)
-        if os.path.exists(src):
-            assert hashlib.sha256(open(src, "rb").read()).digest() == hashlib.sha256(open(os.path.join(build_ref.DST, rel), "rb").read()).digest(), rel
+    with zipfile.ZipFile(build_ref.ARCHIVE) as z:
+        assert sorted(z.namelist()) == sorted(build_ref.FILES)
+        for rel in build_ref.FILES:
+            src = os.path.join("/root/reference", rel)
+            if os.path.exists(src):
+                assert z.read(rel) == open(src, "rb").read(), rel
+    assert not os.path.isdir(os.path.join(build_ref.DST, "gato")), "loose reference sources under oracle/_ref"
     code = ("from oracle import ref_shim; assert ref_shim.reference_kind() == 'vendored', ref_shim.REFERENCE_ROOT; "
             "G = ref_shim.load_reference_policy_class(); "
-            "m = G(device='cpu', embed_dim=32, layers=1, heads=1, dropout=0.0, resid_mid_channels=128, context_len=32); print('ok')")
+            "m = G(device='cpu', embed_dim=32, layers=1, heads=1, dropout=0.0, resid_mid_channels=128, context_len=32); "
+            "l, loss = m([{'text': [1, 2, 3]}], compute_loss=True); loss.backward(); print('ok')")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT,
-                         env=dict(os.environ, NEKO_REFERENCE_ROOT=build_ref.DST))
+                         env=dict(os.environ, NEKO_REFERENCE_ROOT=build_ref.ARCHIVE))
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]
     # oracle/_ref must stay out of the history
     assert "oracle/_ref/" in open(os.path.join(ROOT, ".gitignore")).read()
